@@ -1,0 +1,133 @@
+/* saicv_b200.h — C ABI of libsaicv_b200.so: the sm_100a kernels behind the SimpleAICV
+ * data-parallel training hot path (conv / ViT backbones forward + backward).
+ *
+ * The reference (zgcr/SimpleAICV_pytorch_training_examples) ships no native code; every entry
+ * point below replaces a torch library call made from the reference file:line that is cited.
+ * Conventions: raw device pointers + sizes, `stream` is a cudaStream_t passed as void*, the
+ * library never allocates or frees device memory, never synchronises, never touches the
+ * default stream unless stream == NULL is passed by the caller.  Every function returns 0 on
+ * success and a non-zero code otherwise; saicv_last_error() returns a thread-local message.
+ * Activations are NHWC bf16, parameters are fp32 in the reference's own layouts; bf16 operand
+ * copies of weights are made by saicv_prep_conv_weight / saicv_cast_bf16.
+ */
+#ifndef SAICV_B200_H_
+#define SAICV_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* epilogue flags for the GEMM family */
+#define SAICV_EPI_BIAS 1
+#define SAICV_EPI_RELU 2
+#define SAICV_EPI_GELU 4
+#define SAICV_EPI_DIRECT 8 /* debugging: registers -> global without the TMA store path */
+#define SAICV_EPI_RESID 16 /* += fp32 residual[M, N] */
+
+int saicv_version(void);
+const char* saicv_last_error(void);
+/* Number of SMs the persistent kernels size their grids for (148 on B200). */
+int saicv_sm_count(void);
+
+/* ---- dense layers: nn.Linear (vit.py:57-58,87-89; resnet.py:204) ------------------------ */
+/* y[M,N] = x[M,K] w[N,K]^T (+bias) (+act) (+resid); x,w bf16; y bf16 or fp32 (out_f32). */
+int saicv_linear_fwd(const void* x, const void* w, const float* bias, const float* resid, void* y,
+                     int M, int N, int K, int flags, int out_f32, void* stream);
+/* dx[M,K] = dy[M,N] w[N,K]; dy,w bf16; dx bf16 or fp32 (+resid fp32 [M,K] when flagged). */
+int saicv_linear_dgrad(const void* dy, const void* w, const float* resid, void* dx, int M, int N,
+                       int K, int flags, int out_f32, void* stream);
+/* dw_partial[splits][N][K] (fp32) = dy[M,N]^T x[M,K], reduction over M split `splits` ways.
+ * Pass splits = saicv_wgrad_splits(...) and reduce with saicv_reduce_partials. */
+int saicv_linear_wgrad(const void* dy, const void* x, float* dw_partial, int M, int N, int K,
+                       int splits, void* stream);
+int saicv_wgrad_splits(int out_rows, int out_cols, long long reduce_len);
+
+/* ---- convolutions: nn.Conv2d inside ConvBnActBlock (resnet.py:33-39, darknet.py:49-56) ---- */
+typedef struct {
+  int n, h, w, c; /* input  NHWC */
+  int k, r, s;    /* filters, taps; weights bf16 [k][r][s][c] */
+  int stride, pad;
+} saicv_conv_shape;
+/* y[n,p,q,k] bf16; requires c % 64 == 0 (the 3-channel stem goes through saicv_stem_im2col +
+ * saicv_linear_fwd). */
+int saicv_conv_fprop(const void* x, const void* w, void* y, const saicv_conv_shape* cs, int flags,
+                     void* stream);
+/* dx[n,h,w,c] = sum dy[n, h+pad-r, w+pad-s, k] w[k,r,s,c]: stride-1 data gradient.  For a
+ * stride-2 conv pass the zero-upsampled dy (saicv_zero_upsample) and stride = 1.  `dy` has
+ * spatial extent (h, w).  requires k % 64 == 0, c % 64 == 0. */
+int saicv_conv_dgrad(const void* dy, const void* w, void* dx, const saicv_conv_shape* cs,
+                     void* stream);
+/* dw_partial[splits][k][r*s*c] fp32 = sum over output pixels dy[pix,k] * x[patch(pix), (r,s,c)]. */
+int saicv_conv_wgrad(const void* dy, const void* x, float* dw_partial, const saicv_conv_shape* cs,
+                     int splits, void* stream);
+
+/* ---- layout / weight preparation ---------------------------------------------------------- */
+/* fp32 [k][c][r][s] (torch Conv2d.weight) -> bf16 [k][kpad] with column (r*s_+s)*c_ + c, zero
+ * padded to kpad (kpad >= r*s*c, multiple of 8). */
+int saicv_prep_conv_weight(const float* w, void* w_bf16, int k, int c, int r, int s, int kpad,
+                           void* stream);
+/* sum of fp32 partials [splits][k][kpad] -> fp32 grad in torch layout [k][c][r][s];
+ * accumulate != 0 adds to the destination (gradient accumulation). */
+int saicv_finish_conv_wgrad(const float* partial, float* grad, int splits, int k, int c, int r,
+                            int s, int kpad, int accumulate, void* stream);
+/* out[i] (+)= sum_s partial[s][i]; plain reduction for linear wgrad. */
+int saicv_reduce_partials(const float* partial, float* out, int splits, long long n,
+                          int accumulate, void* stream);
+int saicv_cast_bf16(const float* src, void* dst, long long n, void* stream);
+/* NCHW fp32 image batch -> NHWC bf16 */
+int saicv_nchw_to_nhwc_bf16(const float* x, void* y, int n, int c, int h, int w, void* stream);
+/* NCHW fp32 image batch -> im2col matrix [n*p*q][kpad] bf16 for the 3-channel stem conv
+ * (resnet.py:173-180 7x7/2, resnetforcifar.py:38-45 3x3/1); column (r*s_+s)*c + ch. */
+int saicv_stem_im2col(const float* x, void* cols, int n, int c, int h, int w, int r, int s,
+                      int stride, int pad, int kpad, void* stream);
+/* u[n, 2p, 2q, c] = dy[n,p,q,c], zero elsewhere; u is [n,h,w,c]. */
+int saicv_zero_upsample2(const void* dy, void* u, int n, int p, int q, int h, int w, int c,
+                         void* stream);
+/* dx[n,2p,2q,c] += dd[n,p,q,c]  (data gradient of a 1x1 stride-2 conv added in place). */
+int saicv_add_strided2(void* dx, const void* dd, int n, int p, int q, int h, int w, int c,
+                       void* stream);
+
+/* ---- BatchNorm2d (training) + ReLU + residual (resnet.py:40-42,152-153) ------------------- */
+/* per-channel sum / sum of squares of y[rows][c] (bf16) into stats[2][c] (fp32; zeroed by
+ * the call itself on `stream` before the reduction). */
+int saicv_bn_stats(const void* y, float* stats, long long rows, int c, void* stream);
+/* mean/var from stats -> scale_shift[2][c], saved[2][c] = (mean, rstd); running stats updated
+ * with `momentum` and the unbiased variance exactly like nn.BatchNorm2d; stats zeroed. */
+int saicv_bn_finalize(float* stats, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, float* scale_shift, float* saved, long long rows, int c,
+                      float eps, float momentum, void* stream);
+/* out = act(y*scale+shift + res) ; res optional, itself optionally batch-normalised with
+ * res_scale_shift (downsample branch).  act: 0 none, 1 ReLU, 2 LeakyReLU(0.1). */
+int saicv_bn_apply(const void* y, const float* scale_shift, const void* res,
+                   const float* res_scale_shift, void* out, long long rows, int c, int act,
+                   void* stream);
+/* backward reductions: g = dout * act'(out); sums[0][c] = sum g, sums[1][c] = sum g * xhat
+ * (xhat from y, saved mean/rstd).  `out` (activated output) may be NULL when act == 0.
+ * sums is zeroed by the call itself on `stream`. */
+int saicv_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* saved,
+                        float* sums, long long rows, int c, int act, void* stream);
+/* dy = gamma*rstd*(g - sum_g/rows - xhat*sum_gx/rows) bf16; writes dgamma/dbeta (fp32, (+)=)
+ * and optionally dres = g (gradient flowing into the residual input). */
+int saicv_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* saved,
+                       const float* gamma, float* sums, void* dy, void* dres, float* dgamma,
+                       float* dbeta, long long rows, int c, int act, int accumulate, void* stream);
+/* a = a + b (bf16), used where two gradient paths meet. */
+int saicv_add_bf16(void* a, const void* b, long long n, void* stream);
+
+/* ---- pooling (resnet.py:184,203) ----------------------------------------------------------- */
+int saicv_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, int n, int h, int w, int c,
+                           void* stream);
+int saicv_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int n, int h, int w,
+                           int c, void* stream);
+int saicv_avgpool_fwd(const void* x, void* y, int n, int hw, int c, void* stream);
+int saicv_avgpool_bwd(const void* dy, void* dx, int n, int hw, int c, void* stream);
+/* column sums of a bf16 (or fp32 when is_f32) [rows][c] matrix into fp32 out[c] ((+)= when
+ * accumulate): bias gradients. */
+int saicv_colsum(const void* x, float* out, long long rows, int c, int accumulate, int is_f32,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAICV_B200_H_ */

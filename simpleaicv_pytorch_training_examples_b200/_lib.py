@@ -1,0 +1,87 @@
+"""ctypes binding of libsaicv_b200.so (the C ABI in include/saicv_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (``make -C csrc``).  There is no
+fallback: if the shared object is missing, or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsaicv_b200.so')
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_float = ctypes.c_float
+
+
+class ConvShape(ctypes.Structure):
+    """saicv_conv_shape (include/saicv_b200.h)."""
+    _fields_ = [('n', c_int), ('h', c_int), ('w', c_int), ('c', c_int),
+                ('k', c_int), ('r', c_int), ('s', c_int), ('stride', c_int),
+                ('pad', c_int)]
+
+
+# name -> argtypes; every symbol declared in include/saicv_b200.h is listed here and
+# tests/test_capi_symbols.py checks the header, this table and the .so agree.
+SIGNATURES = {
+    'saicv_version': [],
+    'saicv_sm_count': [],
+    'saicv_linear_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_linear_dgrad': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_linear_wgrad': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_wgrad_splits': [c_int, c_int, c_ll],
+    'saicv_conv_fprop': [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvShape), c_int, c_void_p],
+    'saicv_conv_dgrad': [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvShape), c_void_p],
+    'saicv_conv_wgrad': [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvShape), c_int, c_void_p],
+    'saicv_prep_conv_weight': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_finish_conv_wgrad': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_reduce_partials': [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p],
+    'saicv_cast_bf16': [c_void_p, c_void_p, c_ll, c_void_p],
+    'saicv_nchw_to_nhwc_bf16': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_stem_im2col': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_zero_upsample2': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_add_strided2': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_bn_stats': [c_void_p, c_void_p, c_ll, c_int, c_void_p],
+    'saicv_bn_finalize': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_float, c_void_p],
+    'saicv_bn_apply': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p],
+    'saicv_bn_bwd_reduce': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p],
+    'saicv_bn_bwd_apply': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
+    'saicv_add_bf16': [c_void_p, c_void_p, c_ll, c_void_p],
+    'saicv_maxpool3x3s2_fwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_maxpool3x3s2_bwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_avgpool_fwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    'saicv_avgpool_bwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    'saicv_colsum': [c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(there is no CPU or library fallback for the hot path)')
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.saicv_last_error.restype = ctypes.c_char_p
+    lib.saicv_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f'{name} failed ({rc}): {lib.saicv_last_error().decode()}')
+    return rc

@@ -1,0 +1,387 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution engine for sm_100a.
+//
+//   D[M, N] (+ split-K partials) = A[M, K] * B[N, K]^T     bf16 x bf16 -> fp32 (TMEM)
+//
+// One CTA per SM, 256 threads:
+//   warp 0      TMA producer (one lane)        global -> 128B-swizzled smem ring
+//   warp 1      MMA issuer   (one lane)        tcgen05.mma, accumulators double-buffered in TMEM
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue: tcgen05.ld -> registers -> (bias/act) -> smem -> TMA store
+//
+// Operand feeding modes (runtime, so that fprop / dgrad / wgrad of linear layers and of NHWC
+// convolutions all go through this one kernel):
+//   A_K2D    A is a row-major [M, K] matrix                      (linear fwd / dgrad, 1x1 conv)
+//   A_IM2COL A is an NHWC activation tensor read with TMA im2col (conv fprop / dgrad)
+//   A_MN2D   A is stored [K, M] (K = reduction over pixels)      (wgrad: dY^T)
+//   B_K2D    B is a row-major [N, K] matrix                      (weights, fprop)
+//   B_MN2D   B is stored [K, N]                                  (weights for dgrad, x for wgrad)
+//   B_IM2COL B is an NHWC tensor read with TMA im2col, [pixels, C] (wgrad of a conv)
+#pragma once
+#include "ptx.cuh"
+
+namespace saicv {
+
+enum : int { A_K2D = 0, A_IM2COL = 1, A_MN2D = 2 };
+enum : int { B_K2D = 0, B_MN2D = 2, B_IM2COL = 3 };
+enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_GELU = 4, EPI_DIRECT = 8, EPI_RESID = 16 };
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 256;
+constexpr int kStoreBufBytes = 16384;  // 128 rows x 128 B
+constexpr int kSmemBudget = 232448 - 1024 /*align slack*/ - 512 /*barriers*/;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
+  static constexpr int kStagesRaw = (kSmemBudget - 2 * kStoreBufBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStoreBufBytes + 512 + 1024;
+};
+
+struct ConvGeom {
+  // Geometry of the tensor that is read in im2col mode (A for fprop/dgrad, B for wgrad).
+  int P, Q;          // output spatial extent (rows of the implicit GEMM = n*P*Q + p*Q + q)
+  int stride;        // traversal stride
+  int lc_h, lc_w;    // lower corner (= -pad for fprop/wgrad, pad-(R-1) for dgrad)
+  int R, S;          // filter taps
+  int cchunks;       // channels of the im2col tensor / 64
+  int n_img;         // batch (used to push padding tiles out of bounds)
+};
+
+struct GemmParams {
+  int M, N;            // output extent
+  int num_kb;          // total 64-wide reduction blocks
+  int kb_per_split;    // reduction blocks handled by one split
+  int splits;
+  int a_mode, b_mode;
+  int flip_taps;       // dgrad: B tap index is mirrored
+  int b_cin;           // dgrad/fprop: channels per tap in the weight matrix row (Cin)
+  ConvGeom g;
+  uint32_t idesc;
+  int epi_flags;
+  int out_f32;         // 1: D is fp32, else bf16
+  const float* bias;   // [N] or null
+  const float* resid;  // fp32 [M, ldd] residual added in the epilogue (EPI_RESID) or null
+  void* out;           // direct-store path
+  long long ldd;       // leading dimension of D in elements
+  long long split_stride;  // elements between split-K partial outputs
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kABytes = BM * BK * 2;
+  constexpr int kBBytes = BN * BK * 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kABytes;
+  uint8_t* sD = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sD + 2 * kStoreBufBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int total = num_m * num_n * p.splits;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int PQ = p.g.P * p.g.Q;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int n_blk = w % num_n;
+        const int t = w / num_n;
+        const int m_blk = t % num_m;
+        const int split = t / num_m;
+        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        // im2col base pixel of the A tile (fprop / dgrad): fixed for the whole tile
+        int a_n = 0, a_h = 0, a_w = 0;
+        if (p.a_mode == A_IM2COL) {
+          a_n = m0 / PQ;
+          const int rem = m0 - a_n * PQ;
+          const int pp = rem / p.g.Q;
+          a_h = pp * p.g.stride + p.g.lc_h;
+          a_w = (rem - pp * p.g.Q) * p.g.stride + p.g.lc_w;
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint64_t* bar = &full_bar[stage];
+          mbar_expect_tx(bar, kABytes + kBBytes);
+          uint8_t* a_dst = sA + stage * kABytes;
+          uint8_t* b_dst = sB + stage * kBBytes;
+          int tap = 0, cc = kb, r = 0, s = 0;
+          if (p.a_mode == A_IM2COL) {
+            tap = kb / p.g.cchunks;
+            cc = kb - tap * p.g.cchunks;
+            r = tap / p.g.S;
+            s = tap - r * p.g.S;
+          }
+          // ---- A
+          if (p.a_mode == A_K2D) {
+            tma_load_2d(&tmA, bar, a_dst, kb * BK, m0);
+          } else if (p.a_mode == A_IM2COL) {
+            tma_load_im2col_4d(&tmA, bar, a_dst, cc * 64, a_w, a_h, a_n, (uint16_t)s, (uint16_t)r);
+          } else {  // A_MN2D: [K rows, M cols], two 64-wide column chunks
+            tma_load_2d(&tmA, bar, a_dst, m0, kb * BK);
+            tma_load_2d(&tmA, bar, a_dst + 8192, m0 + 64, kb * BK);
+          }
+          // ---- B
+          if (p.b_mode == B_K2D) {
+            tma_load_2d(&tmB, bar, b_dst, kb * BK, n0);
+          } else if (p.b_mode == B_MN2D) {
+            int col_base = 0, row = kb * BK;
+            if (p.a_mode == A_IM2COL) {  // conv dgrad: weights [Cout, R*S*Cin], mirrored tap
+              const int tapb = p.flip_taps ? (p.g.R * p.g.S - 1 - tap) : tap;
+              col_base = tapb * p.b_cin;
+              row = cc * 64;
+            }
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(&tmB, bar, b_dst + j * 8192, col_base + n0 + j * 64, row);
+          } else {  // B_IM2COL (wgrad): reduction rows = 64 output pixels starting at kb*64
+            const int pix = kb * BK;
+            const int bn_ = pix / PQ;
+            const int rem = pix - bn_ * PQ;
+            const int pp = rem / p.g.Q;
+            const int bh = pp * p.g.stride + p.g.lc_h;
+            const int bw = (rem - pp * p.g.Q) * p.g.stride + p.g.lc_w;
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              const int cb = n0 / 64 + j;
+              const int tapj = cb / p.g.cchunks;
+              const int ccj = cb - tapj * p.g.cchunks;
+              const int rj = tapj / p.g.S;
+              const int sj = tapj - rj * p.g.S;
+              const bool valid = tapj < p.g.R * p.g.S;
+              tma_load_im2col_4d(&tmB, bar, b_dst + j * 8192, ccj * 64, bw, bh,
+                                 valid ? bn_ : p.g.n_img, (uint16_t)(valid ? sj : 0),
+                                 (uint16_t)(valid ? rj : 0));
+            }
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      const bool a_mn = (p.a_mode == A_MN2D);
+      const bool b_mn = (p.b_mode != B_K2D);
+      const uint32_t a_lbo = a_mn ? 8192u : 16u;
+      const uint32_t b_lbo = b_mn ? 8192u : 16u;
+      const uint32_t a_kstep = a_mn ? 2048u : 32u;  // bytes per UMMA_K=16 step
+      const uint32_t b_kstep = b_mn ? 2048u : 32u;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int split = (w / num_n) / num_m;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * kABytes);
+          const uint32_t b_addr = smem_u32(sB + stage * kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024);
+            umma_bf16(d_tmem, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================================================ epilogue
+    const int q = warp & 3;  // TMEM sub-partition of this warp
+    const int epi_tid = threadIdx.x - 128;
+    const int row_in_tile = q * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    int sbuf = 0;
+    const bool direct = (p.epi_flags & EPI_DIRECT) != 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int n_blk = w % num_n;
+      const int t = w / num_n;
+      const int m_blk = t % num_m;
+      const int split = t / num_m;
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const long long row = m0 + row_in_tile;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          // all accumulator columns of this buffer are in registers: hand TMEM back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        const int col0 = n0 + c * 32;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.epi_flags & EPI_BIAS) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.epi_flags & EPI_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        }
+        if (p.epi_flags & EPI_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if ((p.epi_flags & EPI_RESID) && row < p.M) {
+          const float* rp = p.resid + row * p.ldd + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < p.N) {
+              const float4 rv = *reinterpret_cast<const float4*>(rp + j);
+              f[j] += rv.x; f[j + 1] += rv.y; f[j + 2] += rv.z; f[j + 3] += rv.w;
+            }
+          }
+        }
+        if (direct) {
+          if (row < p.M) {
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + split * p.split_stride + row * p.ldd + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (col0 + j < p.N)
+                  *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + split * p.split_stride +
+                                 row * p.ldd + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                if (col0 + j < p.N)
+                  *reinterpret_cast<uint4*>(o + j) =
+                      make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
+                                 pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
+            }
+          }
+        } else if (p.out_f32) {
+          // one 128 B (32 x fp32) slice per TMA store
+          if (epi_tid == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          uint8_t* buf = sD + sbuf * kStoreBufBytes + row_in_tile * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(buf + ((j ^ (row_in_tile & 7)) << 4)) =
+                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (epi_tid == 0) {
+            if (col0 < p.N) {
+              asm volatile(
+                  "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                      reinterpret_cast<uint64_t>(&tmD)),
+                  "r"(smem_u32(sD + sbuf * kStoreBufBytes)), "r"(col0), "r"(m0), "r"(split)
+                  : "memory");
+            }
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+        } else {
+          // bf16: two 32-column chunks make one 128 B (64 x bf16) slice
+          const int half = c & 1;
+          if (half == 0) {
+            if (epi_tid == 0) tma_store_wait_read<1>();
+            named_bar_sync(1, 128);
+          }
+          uint8_t* buf = sD + sbuf * kStoreBufBytes + row_in_tile * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(buf + (((half * 4 + j) ^ (row_in_tile & 7)) << 4)) =
+                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+          if (half == 1 || c == BN / 32 - 1) {
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (epi_tid == 0) {
+              const int scol = n0 + (c >> 1) * 64;
+              if (scol < p.N) {
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                        reinterpret_cast<uint64_t>(&tmD)),
+                    "r"(smem_u32(sD + sbuf * kStoreBufBytes)), "r"(scol), "r"(m0), "r"(split)
+                    : "memory");
+              }
+              tma_store_commit();
+            }
+            sbuf ^= 1;
+          }
+        }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (epi_tid == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+}  // namespace saicv

@@ -1,0 +1,9 @@
+// Error reporting shared by the translation units of libsaicv_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace saicv {
+// Formats into a thread-local buffer returned by saicv_last_error(); always returns 1.
+int set_error(const char* fmt, ...);
+int check_launch(const char* what);
+}  // namespace saicv

@@ -1,0 +1,238 @@
+"""Tensor-level wrappers over the C ABI: torch is used for device memory and streams only.
+
+Every function launches on torch's current CUDA stream and returns immediately.  Tensors must be
+contiguous CUDA tensors; activations are NHWC bf16 (a conv activation of logical shape
+[N, C, H, W] is held as a [N, H, W, C] contiguous tensor).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvShape
+
+EPI_BIAS, EPI_RELU, EPI_GELU, EPI_DIRECT, EPI_RESID = 1, 2, 4, 8, 16
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'saicv ops need contiguous CUDA tensors'
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def conv_out_size(h, pad, r, stride):
+    return (h + 2 * pad - r) // stride + 1
+
+
+def make_conv_shape(n, h, w, c, k, r, s, stride, pad):
+    return ConvShape(n, h, w, c, k, r, s, stride, pad)
+
+
+# ----------------------------------------------------------------------------- dense layers
+def linear_fwd(x, w, bias=None, resid=None, out=None, flags=0, out_f32=False):
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == K
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    _lib.call('saicv_linear_fwd', _p(x), _p(w), _p(bias), _p(resid), _p(out), M, N, K, flags,
+              int(out_f32), _stream())
+    return out
+
+
+def linear_dgrad(dy, w, resid=None, out=None, flags=0, out_f32=False):
+    M, N = dy.shape
+    K = w.shape[1]
+    assert dy.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[0] == N
+    if out is None:
+        out = torch.empty(M, K, device=dy.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    _lib.call('saicv_linear_dgrad', _p(dy), _p(w), _p(resid), _p(out), M, N, K, flags, int(out_f32),
+              _stream())
+    return out
+
+
+def wgrad_splits(out_rows, out_cols, reduce_len):
+    return _lib.load().saicv_wgrad_splits(out_rows, out_cols, reduce_len)
+
+
+def linear_wgrad(dy, x, partial=None):
+    """Returns fp32 partials [splits, N, K]; reduce with reduce_partials."""
+    M, N = dy.shape
+    K = x.shape[1]
+    splits = wgrad_splits(N, K, M)
+    if partial is None:
+        partial = torch.empty(splits, N, K, device=dy.device, dtype=torch.float32)
+    _lib.call('saicv_linear_wgrad', _p(dy), _p(x), _p(partial), M, N, K, splits, _stream())
+    return partial
+
+
+def reduce_partials(partial, out, accumulate=False):
+    splits = partial.shape[0]
+    n = out.numel()
+    _lib.call('saicv_reduce_partials', _p(partial), _p(out), splits, n, int(accumulate), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- convolutions
+def conv_fprop(x, w, cs, out=None, flags=0):
+    P = conv_out_size(cs.h, cs.pad, cs.r, cs.stride)
+    Q = conv_out_size(cs.w, cs.pad, cs.s, cs.stride)
+    if out is None:
+        out = torch.empty(cs.n, P, Q, cs.k, device=x.device, dtype=torch.bfloat16)
+    _lib.call('saicv_conv_fprop', _p(x), _p(w), _p(out), ctypes.byref(cs), flags, _stream())
+    return out
+
+
+def conv_dgrad(dy, w, cs, out=None):
+    """dy: [n, h, w, k] (zero-upsampled for strided convs); cs.stride must be 1."""
+    if out is None:
+        out = torch.empty(cs.n, cs.h, cs.w, cs.c, device=dy.device, dtype=torch.bfloat16)
+    _lib.call('saicv_conv_dgrad', _p(dy), _p(w), _p(out), ctypes.byref(cs), _stream())
+    return out
+
+
+def conv_wgrad(dy, x, cs, partial=None):
+    P = conv_out_size(cs.h, cs.pad, cs.r, cs.stride)
+    Q = conv_out_size(cs.w, cs.pad, cs.s, cs.stride)
+    ncols = cs.r * cs.s * cs.c
+    splits = wgrad_splits(cs.k, ncols, cs.n * P * Q)
+    if partial is None:
+        partial = torch.empty(splits, cs.k, ncols, device=dy.device, dtype=torch.float32)
+    _lib.call('saicv_conv_wgrad', _p(dy), _p(x), _p(partial), ctypes.byref(cs), splits, _stream())
+    return partial
+
+
+def prep_conv_weight(w_f32, out, kpad):
+    k, c, r, s = w_f32.shape
+    _lib.call('saicv_prep_conv_weight', _p(w_f32), _p(out), k, c, r, s, kpad, _stream())
+    return out
+
+
+def finish_conv_wgrad(partial, grad, kpad, accumulate=False):
+    k, c, r, s = grad.shape
+    _lib.call('saicv_finish_conv_wgrad', _p(partial), _p(grad), partial.shape[0], k, c, r, s, kpad,
+              int(accumulate), _stream())
+    return grad
+
+
+def cast_bf16(src, out=None):
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    _lib.call('saicv_cast_bf16', _p(src), _p(out), src.numel(), _stream())
+    return out
+
+
+def nchw_to_nhwc_bf16(x, out=None):
+    n, c, h, w = x.shape
+    if out is None:
+        out = torch.empty(n, h, w, c, device=x.device, dtype=torch.bfloat16)
+    _lib.call('saicv_nchw_to_nhwc_bf16', _p(x), _p(out), n, c, h, w, _stream())
+    return out
+
+
+def stem_im2col(x, r, s, stride, pad, kpad, out=None):
+    n, c, h, w = x.shape
+    P, Q = conv_out_size(h, pad, r, stride), conv_out_size(w, pad, s, stride)
+    if out is None:
+        out = torch.empty(n * P * Q, kpad, device=x.device, dtype=torch.bfloat16)
+    _lib.call('saicv_stem_im2col', _p(x), _p(out), n, c, h, w, r, s, stride, pad, kpad, _stream())
+    return out
+
+
+def zero_upsample2(dy, h, w, out=None):
+    n, p, q, c = dy.shape
+    if out is None:
+        out = torch.empty(n, h, w, c, device=dy.device, dtype=torch.bfloat16)
+    _lib.call('saicv_zero_upsample2', _p(dy), _p(out), n, p, q, h, w, c, _stream())
+    return out
+
+
+def add_strided2(dx, dd):
+    n, h, w, c = dx.shape
+    _, p, q, _ = dd.shape
+    _lib.call('saicv_add_strided2', _p(dx), _p(dd), n, p, q, h, w, c, _stream())
+    return dx
+
+
+# ----------------------------------------------------------------------------- batch norm
+def bn_stats(y, stats):
+    c = y.shape[-1]
+    _lib.call('saicv_bn_stats', _p(y), _p(stats), y.numel() // c, c, _stream())
+
+
+def bn_finalize(stats, gamma, beta, rmean, rvar, scale_shift, saved, rows, eps, momentum):
+    c = gamma.numel()
+    _lib.call('saicv_bn_finalize', _p(stats), _p(gamma), _p(beta), _p(rmean), _p(rvar),
+              _p(scale_shift), _p(saved), rows, c, eps, momentum, _stream())
+
+
+def bn_apply(y, scale_shift, out, act, res=None, res_scale_shift=None):
+    c = y.shape[-1]
+    _lib.call('saicv_bn_apply', _p(y), _p(scale_shift), _p(res), _p(res_scale_shift), _p(out),
+              y.numel() // c, c, act, _stream())
+    return out
+
+
+def bn_bwd_reduce(dout, out, y, saved, sums, act):
+    c = y.shape[-1]
+    _lib.call('saicv_bn_bwd_reduce', _p(dout), _p(out), _p(y), _p(saved), _p(sums), y.numel() // c, c,
+              act, _stream())
+
+
+def bn_bwd_apply(dout, out, y, saved, gamma, sums, dy, dres, dgamma, dbeta, act, accumulate=False):
+    c = y.shape[-1]
+    _lib.call('saicv_bn_bwd_apply', _p(dout), _p(out), _p(y), _p(saved), _p(gamma), _p(sums), _p(dy),
+              _p(dres), _p(dgamma), _p(dbeta), y.numel() // c, c, act, int(accumulate), _stream())
+
+
+def add_bf16(a, b):
+    _lib.call('saicv_add_bf16', _p(a), _p(b), a.numel(), _stream())
+    return a
+
+
+# ----------------------------------------------------------------------------- pooling
+def maxpool3x3s2_fwd(x, out=None, argmax=None):
+    n, h, w, c = x.shape
+    P, Q = conv_out_size(h, 1, 3, 2), conv_out_size(w, 1, 3, 2)
+    if out is None:
+        out = torch.empty(n, P, Q, c, device=x.device, dtype=torch.bfloat16)
+    if argmax is None:
+        argmax = torch.empty(n, P, Q, c, device=x.device, dtype=torch.uint8)
+    _lib.call('saicv_maxpool3x3s2_fwd', _p(x), _p(out), _p(argmax), n, h, w, c, _stream())
+    return out, argmax
+
+
+def maxpool3x3s2_bwd(dy, argmax, h, w, out=None):
+    n, _, _, c = dy.shape
+    if out is None:
+        out = torch.empty(n, h, w, c, device=dy.device, dtype=torch.bfloat16)
+    _lib.call('saicv_maxpool3x3s2_bwd', _p(dy), _p(argmax), _p(out), n, h, w, c, _stream())
+    return out
+
+
+def avgpool_fwd(x, out=None):
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty(n, c, device=x.device, dtype=torch.bfloat16)
+    _lib.call('saicv_avgpool_fwd', _p(x), _p(out), n, h * w, c, _stream())
+    return out
+
+
+def avgpool_bwd(dy, h, w, out=None):
+    n, c = dy.shape
+    if out is None:
+        out = torch.empty(n, h, w, c, device=dy.device, dtype=torch.bfloat16)
+    _lib.call('saicv_avgpool_bwd', _p(dy), _p(out), n, h * w, c, _stream())
+    return out
+
+
+def colsum(x, out, accumulate=False):
+    c = x.shape[-1]
+    _lib.call('saicv_colsum', _p(x), _p(out), x.numel() // c, c, int(accumulate),
+              int(x.dtype == torch.float32), _stream())
+    return out
