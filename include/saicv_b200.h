@@ -29,6 +29,8 @@ int saicv_version(void);
 const char* saicv_last_error(void);
 /* Number of SMs the persistent kernels size their grids for (148 on B200). */
 int saicv_sm_count(void);
+/* Kernels launched by this library in this process so far (bench.py reports the delta). */
+long long saicv_launch_count(void);
 
 /* ---- dense layers: nn.Linear (vit.py:57-58,87-89; resnet.py:204) ------------------------ */
 /* y[M,N] = x[M,K] w[N,K]^T (+bias) (+act) (+resid); x,w bf16; y bf16 or fp32 (out_f32). */

@@ -70,12 +70,19 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.saicv_last_error.restype = ctypes.c_char_p
     lib.saicv_last_error.argtypes = []
+    lib.saicv_launch_count.restype = c_ll
+    lib.saicv_launch_count.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_int
     _lib = lib
     return lib
+
+
+def launch_count():
+    """Kernels launched by the library so far in this process."""
+    return int(load().saicv_launch_count())
 
 
 def call(name, *args):

@@ -96,6 +96,10 @@ class _ResNetBase(nn.Module):
             self.__dict__['_rt'] = rt  # not a submodule / not in state_dict
         return rt
 
+    def grad_sink(self):
+        """Where the runtime deposits parameter gradients (used by distributed.B200DataParallel)."""
+        return self._runtime().sink
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError('this model runs on B200 kernels only; move the batch to the GPU '

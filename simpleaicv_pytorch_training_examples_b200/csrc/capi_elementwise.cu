@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -21,12 +22,17 @@ int set_error(const char* fmt, ...) {
   va_end(ap);
   return 1;
 }
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("%s: %s", what, cudaGetErrorString(e));
+  count_launch(1);
   return 0;
 }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 const char* last_error() { return g_err; }
+long long launch_count();
 
 namespace {
 
@@ -553,6 +559,7 @@ using namespace saicv;
 extern "C" {
 
 int saicv_version(void) { return 100; }
+long long saicv_launch_count(void) { return saicv::launch_count(); }
 const char* saicv_last_error(void) { return saicv::last_error(); }
 
 int saicv_bn_stats(const void* y, float* stats, long long rows, int c, void* stream) {

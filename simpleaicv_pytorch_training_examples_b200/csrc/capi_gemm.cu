@@ -137,6 +137,7 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, con
   gemm_sm100_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a, b, d, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm_sm100_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
+  count_launch(1);
   return 0;
 }
 

@@ -33,6 +33,7 @@ class GradSink:
     def __init__(self):
         self.views = {}       # id(param) -> fp32 tensor view with the parameter's shape
         self.on_ready = None  # callback(param) fired as soon as a gradient is complete
+        self.on_backward_end = None  # callback() fired when the whole backward pass is enqueued
 
     def buffer_for(self, param):
         v = self.views.get(id(param))
@@ -337,6 +338,8 @@ class ResNetRT:
             da = ops.maxpool3x3s2_bwd(da, tape['argmax'], ph, pw)
         dy, _ = self.stem.bn_bwd(da, tape['stem'], sink)
         self.stem.conv_bwd(dy, tape['stem'], sink, need_dx=False)
+        if sink.on_backward_end is not None:
+            sink.on_backward_end()
 
 
 class _NetFunction(torch.autograd.Function):
