@@ -1,0 +1,117 @@
+"""train / test loops of the classification task with the call signatures of the reference's
+tools/scripts.py:36-113 (test_classification) and :116-275 (train_classification).
+
+Arithmetic per step is the reference's: forward, criterion, backward (gradient average across
+ranks), optional clipping, optimizer step, per-iteration LR.  Control flow is tightened for a
+B200: the NaN/Inf guards are evaluated on the device and travel, together with the loss, in ONE
+small all-reduce and ONE device->host read per step; there is no per-step barrier.
+"""
+import torch
+import torch.distributed as dist
+
+
+class AverageMeter:
+    def __init__(self):
+        self.val = self.avg = self.sum = self.count = 0
+
+    def update(self, val, n=1):
+        self.val = val
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / self.count
+
+
+def _world():
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def all_reduce_operation_in_group_for_variables(variables, operator, group):
+    """tools/scripts.py:26-33, but all scalars share one tensor / one collective / one sync."""
+    t = torch.tensor([float(v) for v in variables], device='cuda', dtype=torch.float64)
+    if dist.is_initialized() and _world() > 1:
+        dist.all_reduce(t, op=operator, group=group)
+    return t.tolist()
+
+
+def _is_master(config):
+    return config.local_rank == 0 and getattr(config, 'total_rank', 0) == 0
+
+
+def train_classification(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config):
+    losses = AverageMeter()
+    model.train()
+    accum = config.accumulation_steps
+    assert accum >= 1, 'illegal accumulation_steps!'
+    iters = len(train_loader.dataset) // config.batch_size
+    group = getattr(config, 'group', None)
+    world = _world()
+    iter_index = 1
+    for _, data in enumerate(train_loader):
+        images = data['image'].cuda(non_blocking=True)
+        labels = data['label'].cuda(non_blocking=True)
+        bad = (~torch.isfinite(images)).any()
+        if labels.dtype.is_floating_point:
+            bad = bad | (~torch.isfinite(labels)).any()
+        outputs = model(images)
+        loss = criterion(outputs, labels)
+        bad = bad | (~torch.isfinite(loss)) | (loss == 0.)
+        loss = loss / accum
+        sync_step = iter_index % accum == 0
+        if sync_step or not hasattr(model, 'no_sync'):
+            loss.backward()
+        else:
+            with model.no_sync():
+                loss.backward()
+        if getattr(config, 'skip_inf_nan_grad', False):
+            for p in model.parameters():
+                if p.grad is not None:
+                    bad = bad | (~torch.isfinite(p.grad)).any()
+        stat = torch.stack([bad.float(), loss.detach().float()])
+        if world > 1:
+            dist.all_reduce(stat, op=dist.ReduceOp.SUM, group=group)
+        skip_count, loss_sum = stat.tolist()  # the one host sync of the step
+        if skip_count > 0:
+            logger.info('skip this batch!') if _is_master(config) else None
+            optimizer.zero_grad()
+            continue
+        if sync_step:
+            if getattr(config, 'clip_grad_value', 0) and config.clip_grad_value > 0:
+                torch.nn.utils.clip_grad_value_(model.parameters(), config.clip_grad_value)
+            if getattr(config, 'clip_max_norm', 0) and config.clip_max_norm > 0:
+                torch.nn.utils.clip_grad_norm_(model.parameters(), config.clip_max_norm)
+            optimizer.step()
+            optimizer.zero_grad()
+            if getattr(config, 'use_ema_model', False):
+                config.ema_model.update(model)
+            loss_value = loss_sum / world
+            losses.update(loss_value, images.size(0))
+            scheduler.step(optimizer, iter_index / iters + (epoch - 1))
+        if iter_index % int(config.print_interval * accum) == 0 and _is_master(config):
+            logger.info(f'train: epoch {epoch:0>4d}, iter [{iter_index // accum:0>5d}, {iters // accum:0>5d}], '
+                        f'lr: {scheduler.current_lr:.6f}, loss: {loss_sum / world * accum:.4f}')
+        iter_index += 1
+    return losses.avg * accum
+
+
+@torch.no_grad()
+def test_classification(test_loader, model, criterion, config):
+    """Returns (acc1 %, acc5 %, loss); top-k indices come from torch.topk like the reference
+    (tools/scripts.py:74-95) so index ties resolve identically."""
+    model.eval()
+    group = getattr(config, 'group', None)
+    correct1 = correct5 = seen = 0.
+    loss_sum = 0.
+    for data in test_loader:
+        images, labels = data['image'].cuda(non_blocking=True), data['label'].cuda(non_blocking=True)
+        outputs = model(images)
+        loss = criterion(outputs, labels)
+        _, pred = torch.topk(outputs.float(), k=5, dim=1, largest=True, sorted=True)
+        pred = pred.t()
+        hit = pred.eq(labels.view(1, -1).expand_as(pred))
+        correct1 += hit[:1].reshape(-1).float().sum().item()
+        correct5 += hit[:5].reshape(-1).float().sum().item()
+        seen += images.size(0)
+        loss_sum += loss.item() * images.size(0)
+    correct1, correct5, seen, loss_sum = all_reduce_operation_in_group_for_variables(
+        [correct1, correct5, seen, loss_sum], dist.ReduceOp.SUM, group)
+    return correct1 / seen * 100, correct5 / seen * 100, loss_sum / seen
