@@ -55,24 +55,26 @@ typedef struct {
  * saicv_linear_fwd). */
 int saicv_conv_fprop(const void* x, const void* w, void* y, const saicv_conv_shape* cs, int flags,
                      void* stream);
-/* dx[n,h,w,c] = sum dy[n, h+pad-r, w+pad-s, k] w[k,r,s,c]: stride-1 data gradient.  For a
- * stride-2 conv pass the zero-upsampled dy (saicv_zero_upsample) and stride = 1.  `dy` has
- * spatial extent (h, w).  requires k % 64 == 0, c % 64 == 0. */
-int saicv_conv_dgrad(const void* dy, const void* w, void* dx, const saicv_conv_shape* cs,
-                     void* stream);
+/* dx[n,h,w,c] = sum dy[n, h+pad-r, w+pad-s, k] w[k,r,s,c] (+ add[n,h,w,c]): stride-1 data
+ * gradient; `add` (bf16, may be NULL) is the gradient arriving over the shortcut, fused into the
+ * epilogue.  For a stride-2 conv pass the zero-upsampled dy (saicv_zero_upsample2) and stride = 1.
+ * `dy` has spatial extent (h, w).  requires k % 64 == 0, c % 64 == 0. */
+int saicv_conv_dgrad(const void* dy, const void* w, const void* add, void* dx,
+                     const saicv_conv_shape* cs, void* stream);
 /* dw_partial[splits][k][r*s*c] fp32 = sum over output pixels dy[pix,k] * x[patch(pix), (r,s,c)]. */
 int saicv_conv_wgrad(const void* dy, const void* x, float* dw_partial, const saicv_conv_shape* cs,
                      int splits, void* stream);
 
 /* ---- layout / weight preparation ---------------------------------------------------------- */
-/* fp32 [k][c][r][s] (torch Conv2d.weight) -> bf16 [k][kpad] with column (r*s_+s)*c_ + c, zero
- * padded to kpad (kpad >= r*s*c, multiple of 8). */
+/* fp32 [k][c][r][s] (torch Conv2d.weight) -> bf16 [k][kpad], zero padded to kpad (kpad >=
+ * r*s*c, multiple of 8).  order 0: column (r*S+s)*C + c, the implicit-GEMM layout of
+ * saicv_conv_*; order 1: column (c*R+r)*S + s, the layout of saicv_stem_im2col. */
 int saicv_prep_conv_weight(const float* w, void* w_bf16, int k, int c, int r, int s, int kpad,
-                           void* stream);
-/* sum of fp32 partials [splits][k][kpad] -> fp32 grad in torch layout [k][c][r][s];
- * accumulate != 0 adds to the destination (gradient accumulation). */
+                           int order, void* stream);
+/* sum of fp32 partials [splits][k][kpad] (columns in `order`) -> fp32 grad in torch layout
+ * [k][c][r][s]; accumulate != 0 adds to the destination (gradient accumulation). */
 int saicv_finish_conv_wgrad(const float* partial, float* grad, int splits, int k, int c, int r,
-                            int s, int kpad, int accumulate, void* stream);
+                            int s, int kpad, int accumulate, int order, void* stream);
 /* out[i] (+)= sum_s partial[s][i]; plain reduction for linear wgrad. */
 int saicv_reduce_partials(const float* partial, float* out, int splits, long long n,
                           int accumulate, void* stream);
@@ -80,7 +82,8 @@ int saicv_cast_bf16(const float* src, void* dst, long long n, void* stream);
 /* NCHW fp32 image batch -> NHWC bf16 */
 int saicv_nchw_to_nhwc_bf16(const float* x, void* y, int n, int c, int h, int w, void* stream);
 /* NCHW fp32 image batch -> im2col matrix [n*p*q][kpad] bf16 for the 3-channel stem conv
- * (resnet.py:173-180 7x7/2, resnetforcifar.py:38-45 3x3/1); column (r*s_+s)*c + ch. */
+ * (resnet.py:173-180 7x7/2, resnetforcifar.py:38-45 3x3/1; vit.py:31-37 16x16/16 patches);
+ * column (ch*R+r)*S + s. */
 int saicv_stem_im2col(const float* x, void* cols, int n, int c, int h, int w, int r, int s,
                       int stride, int pad, int kpad, void* stream);
 /* u[n, 2p, 2q, c] = dy[n,p,q,c], zero elsewhere; u is [n,h,w,c]. */
@@ -105,15 +108,19 @@ int saicv_bn_apply(const void* y, const float* scale_shift, const void* res,
                    const float* res_scale_shift, void* out, long long rows, int c, int act,
                    void* stream);
 /* backward reductions: g = dout * act'(out); sums[0][c] = sum g, sums[1][c] = sum g * xhat
- * (xhat from y, saved mean/rstd).  `out` (activated output) may be NULL when act == 0.
+ * (xhat from y, saved mean/rstd).  The activation mask comes from `out` (activated output) when
+ * it is non-NULL; otherwise, for a unit without residual input, it is recomputed from
+ * sign(y*scale+shift) using `scale_shift` (saves reading `out`).  Both may be NULL when act == 0.
  * sums is zeroed by the call itself on `stream`. */
 int saicv_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* saved,
-                        float* sums, long long rows, int c, int act, void* stream);
+                        const float* scale_shift, float* sums, long long rows, int c, int act,
+                        void* stream);
 /* dy = gamma*rstd*(g - sum_g/rows - xhat*sum_gx/rows) bf16; writes dgamma/dbeta (fp32, (+)=)
  * and optionally dres = g (gradient flowing into the residual input). */
 int saicv_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* saved,
-                       const float* gamma, float* sums, void* dy, void* dres, float* dgamma,
-                       float* dbeta, long long rows, int c, int act, int accumulate, void* stream);
+                       const float* gamma, const float* scale_shift, float* sums, void* dy,
+                       void* dres, float* dgamma, float* dbeta, long long rows, int c, int act,
+                       int accumulate, void* stream);
 /* a = a + b (bf16), used where two gradient paths meet. */
 int saicv_add_bf16(void* a, const void* b, long long n, void* stream);
 

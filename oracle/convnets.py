@@ -78,23 +78,80 @@ def param_names(sd):
     return [k for k in sd if not (k.endswith('running_mean') or k.endswith('running_var') or k.endswith('num_batches_tracked'))]
 
 
-def _cba(sd, prefix, x, k, stride, act, training):
-    y = F.conv2d(x, sd[f'{prefix}.layer.0.weight'], None, stride, k // 2)
+# ---- optional emulation of the B200 path's storage precision -----------------------------------
+# The kernels keep activations and activation gradients in bf16 and feed bf16 operands to the
+# tensor cores (fp32 accumulation; BN statistics, parameters and parameter gradients in fp32).
+# With emulate_bf16=True the SAME reference algorithm is evaluated with a round-to-bf16 at exactly
+# those storage points (forward and backward), so the GPU result can be compared tightly; without
+# it this is the plain fp32 reference.  (Random-init ResNets amplify bf16 rounding so much that the
+# reference's own autocast(bf16) run differs from its fp32 run by ~0.3 relative L2 in early-layer
+# gradients — see DESIGN.md "Parity".)
+class _RoundBoth(torch.autograd.Function):
+    """bf16 storage of an activation: value rounded forward, its gradient rounded backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+class _RoundValue(torch.autograd.Function):
+    """bf16 operand copy of an fp32 parameter: rounded forward, fp32 gradient passes through."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundGrad(torch.autograd.Function):
+    """gradient stored in bf16 where the forward value is fp32 (dlogits -> fc GEMMs)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def _act_store(x, emu):
+    return _RoundBoth.apply(x) if emu else x
+
+
+def _w_operand(w, emu):
+    return _RoundValue.apply(w) if emu else w
+
+
+def _conv_bn(sd, prefix, x, k, stride, training, emu):
+    """conv (bf16-stored output when emulating) -> training/eval BatchNorm in fp32 (not yet stored)."""
+    y = F.conv2d(x, _w_operand(sd[f'{prefix}.layer.0.weight'], emu), None, stride, k // 2)
+    y = _act_store(y, emu)
     bn = f'{prefix}.layer.1'
     y = F.batch_norm(y, sd[f'{bn}.running_mean'], sd[f'{bn}.running_var'], sd[f'{bn}.weight'], sd[f'{bn}.bias'],
                      training, BN_MOMENTUM, BN_EPS)
     if training:
         sd[f'{bn}.num_batches_tracked'] += 1
-    return F.relu(y) if act else y
+    return y
 
 
-def forward(sd, x, arch, training=True):
+def forward(sd, x, arch, training=True, emulate_bf16=False):
     """Logits of `arch` for the NCHW fp32 batch x; running statistics in `sd` are updated in
     place when training (like nn.BatchNorm2d)."""
+    emu = emulate_bf16
     block, nums, cifar = ARCHS[arch]
     specs, _ = _cba_specs(arch)
     spec = {p: (k, s) for p, _, _, k, s in specs}
-    x = _cba(sd, 'conv1', x, *spec['conv1'], True, training)
+    if emu:
+        x = x.bfloat16().float()
+    x = _act_store(F.relu(_conv_bn(sd, 'conv1', x, *spec['conv1'], training, emu)), emu)
     if not cifar:
         x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     for li in range(4):
@@ -102,12 +159,17 @@ def forward(sd, x, arch, training=True):
             p = f'layer{li + 1}.{bi}'
             inp = x
             names = ['conv1', 'conv2'] + (['conv3'] if block == 'bottleneck' else [])
-            for i, nm in enumerate(names):
+            for nm in names[:-1]:
                 k, s = spec[f'{p}.{nm}']
-                x = _cba(sd, f'{p}.{nm}', x, k, s, i < len(names) - 1, training)
+                x = _act_store(F.relu(_conv_bn(sd, f'{p}.{nm}', x, k, s, training, emu)), emu)
+            k, s = spec[f'{p}.{names[-1]}']
+            x = _conv_bn(sd, f'{p}.{names[-1]}', x, k, s, training, emu)       # no activation before the add
             if f'{p}.downsample_conv' in spec:
                 k, s = spec[f'{p}.downsample_conv']
-                inp = _cba(sd, f'{p}.downsample_conv', inp, k, s, False, training)
-            x = F.relu(x + inp)
-    x = F.adaptive_avg_pool2d(x, (1, 1)).flatten(1)
-    return F.linear(x, sd['fc.weight'], sd['fc.bias'])
+                inp = _conv_bn(sd, f'{p}.downsample_conv', inp, k, s, training, emu)
+            x = _act_store(F.relu(x + inp), emu)
+    x = _act_store(F.adaptive_avg_pool2d(x, (1, 1)).flatten(1), emu)
+    z = F.linear(x, _w_operand(sd['fc.weight'], emu))
+    if emu:
+        z = _RoundGrad.apply(z)
+    return z + sd['fc.bias']

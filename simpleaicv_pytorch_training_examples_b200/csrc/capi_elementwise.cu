@@ -81,61 +81,100 @@ int next_pow2(int v) {
   return p;
 }
 
-// ----------------------------------------------------------------------------- column sums
+// ----------------------------------------------------------------------------- slab kernels
+// All BatchNorm kernels share one thread layout: a block owns a slab of rows; thread (tx, ty)
+// always handles the same 8 channels (vector tx of every row) and walks rows ty, ty+ty_count, ...
+// so per-channel coefficients live in registers for the whole kernel, and UNROLL independent
+// 16-byte loads are in flight per tensor per thread.
+constexpr int UNROLL = 4;
+
+struct SlabGeom {
+  int vpr, tx_count, ty_count;
+  long long rows_per_block;
+};
+
 // MODE 0: sum x, sum x^2 (BN forward statistics)
-// MODE 1: g = dout*act'(out); sum g, sum g*xhat (BN backward reductions)
+// MODE 1: g = dout*act'(.); sum g, sum g*xhat (BN backward reductions)
 // MODE 2: sum x only (bias gradients)
+// Activation mask source for MODE 1: `b` (activated output) when non-null, else recomputed
+// from y with scale/shift `ss` (out = act(y*scale+shift) has the sign of y*scale+shift).
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 colreduce_kernel(const void* __restrict__ a, const void* __restrict__ b, const void* __restrict__ y,
-                 const float* __restrict__ saved, float* __restrict__ out, long long rows, int C,
-                 int tx_count, int act, long long rows_per_block) {
+                 const float* __restrict__ saved, const float* __restrict__ ss, float* __restrict__ out,
+                 long long rows, int C, SlabGeom gm, int act) {
   __shared__ float red[kThreads][17];
-  const int vpr = C >> 3;
-  const int tx = threadIdx.x % tx_count;
-  const int ty = threadIdx.x / tx_count;
-  const int ty_count = kThreads / tx_count;
+  const int vpr = gm.vpr;
+  const int tx = threadIdx.x % gm.tx_count;
+  const int ty = threadIdx.x / gm.tx_count;
+  const int ty_count = gm.ty_count;
   float s0[8], s1[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  long long r1 = r0 + rows_per_block;
+  const long long r0 = (long long)blockIdx.x * gm.rows_per_block;
+  long long r1 = r0 + gm.rows_per_block;
   if (r1 > rows) r1 = rows;
   if (tx < vpr) {
-    float mean[8], rstd[8];
+    float mean[8], rstd[8], sc[8], sh[8];
+    const bool recompute_mask = (MODE == 1) && act != 0 && b == nullptr;
     if (MODE == 1) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         mean[i] = saved[tx * 8 + i];
         rstd[i] = saved[C + tx * 8 + i];
+        sc[i] = recompute_mask ? ss[tx * 8 + i] : 0.f;
+        sh[i] = recompute_mask ? ss[C + tx * 8 + i] : 0.f;
       }
     }
-    for (long long r = r0 + ty; r < r1; r += ty_count) {
-      const long long vi = r * vpr + tx;
-      float fa[8];
-      unpack8(ldg8(a, vi), fa);
-      if (MODE == 0) {
+    for (long long r = r0 + ty; r < r1; r += (long long)ty_count * UNROLL) {
+      V8 va[UNROLL], vb[UNROLL], vy[UNROLL];
+      bool ok[UNROLL];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s0[i] += fa[i];
-          s1[i] += fa[i] * fa[i];
+      for (int u = 0; u < UNROLL; ++u) {
+        const long long rr = r + (long long)u * ty_count;
+        ok[u] = rr < r1;
+        if (ok[u]) {
+          const long long vi = rr * vpr + tx;
+          va[u] = ldg8(a, vi);
+          if (MODE == 1) {
+            vy[u] = ldg8(y, vi);
+            if (act != 0 && !recompute_mask) vb[u] = ldg8(b, vi);
+          }
         }
-      } else if (MODE == 2) {
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s0[i] += fa[i];
-      } else {
-        float fy[8];
-        unpack8(ldg8(y, vi), fy);
-        if (act != 0) {
-          float fo[8];
-          unpack8(ldg8(b, vi), fo);
+      for (int u = 0; u < UNROLL; ++u) {
+        if (!ok[u]) continue;
+        float fa[8];
+        unpack8(va[u], fa);
+        if (MODE == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) fa[i] *= act_grad(fo[i], act);
-        }
+          for (int i = 0; i < 8; ++i) {
+            s0[i] += fa[i];
+            s1[i] += fa[i] * fa[i];
+          }
+        } else if (MODE == 2) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s0[i] += fa[i];
-          s1[i] += fa[i] * (fy[i] - mean[i]) * rstd[i];
+          for (int i = 0; i < 8; ++i) s0[i] += fa[i];
+        } else {
+          float fy[8];
+          unpack8(vy[u], fy);
+          if (act != 0) {
+            if (recompute_mask) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) fa[i] *= act_grad(fy[i] * sc[i] + sh[i], act);
+            } else {
+              float fo[8];
+              unpack8(vb[u], fo);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) fa[i] *= act_grad(fo[i], act);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            s0[i] += fa[i];
+            s1[i] += fa[i] * (fy[i] - mean[i]) * rstd[i];
+          }
         }
       }
     }
@@ -151,8 +190,8 @@ colreduce_kernel(const void* __restrict__ a, const void* __restrict__ b, const v
     for (int t = 1; t < ty_count; ++t) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        s0[i] += red[t * tx_count + tx][i];
-        s1[i] += red[t * tx_count + tx][8 + i];
+        s0[i] += red[t * gm.tx_count + tx][i];
+        s1[i] += red[t * gm.tx_count + tx][8 + i];
       }
     }
 #pragma unroll
@@ -163,18 +202,32 @@ colreduce_kernel(const void* __restrict__ a, const void* __restrict__ b, const v
   }
 }
 
+bool slab_geom(long long rows, int C, int min_rows_per_thread, SlabGeom* g, int* blocks) {
+  if (C % 8 || C > 2048) {
+    set_error("BatchNorm / column kernels need C %% 8 == 0 and C <= 2048 (C=%d)", C);
+    return false;
+  }
+  g->vpr = C / 8;
+  g->tx_count = next_pow2(g->vpr) > kThreads ? kThreads : next_pow2(g->vpr);
+  g->ty_count = kThreads / g->tx_count;
+  long long b = (rows + (long long)g->ty_count * min_rows_per_thread - 1) / ((long long)g->ty_count * min_rows_per_thread);
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  g->rows_per_block = (rows + b - 1) / b;
+  // keep slabs a multiple of ty_count*UNROLL rows so only the last block has a ragged tail
+  const long long q = (long long)g->ty_count * UNROLL;
+  g->rows_per_block = (g->rows_per_block + q - 1) / q * q;
+  *blocks = (int)((rows + g->rows_per_block - 1) / g->rows_per_block);
+  return true;
+}
+
 template <int MODE>
-int launch_colreduce(const void* a, const void* b, const void* y, const float* saved, float* out,
-                     long long rows, int C, int act, cudaStream_t st) {
-  if (C % 8 || C > 2048) return set_error("column reduction needs C %% 8 == 0 and C <= 2048 (C=%d)", C);
-  const int tx_count = next_pow2(C / 8) > kThreads ? kThreads : next_pow2(C / 8);
-  const int ty_count = kThreads / tx_count;
-  long long blocks = (rows + ty_count * 8 - 1) / (ty_count * 8);  // >= 8 rows per thread
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  const long long rpb = (rows + blocks - 1) / blocks;
-  blocks = (rows + rpb - 1) / rpb;
-  colreduce_kernel<MODE><<<(int)blocks, kThreads, 0, st>>>(a, b, y, saved, out, rows, C, tx_count, act, rpb);
+int launch_colreduce(const void* a, const void* b, const void* y, const float* saved, const float* ss,
+                     float* out, long long rows, int C, int act, cudaStream_t st) {
+  SlabGeom g;
+  int blocks;
+  if (!slab_geom(rows, C, 2 * UNROLL, &g, &blocks)) return 1;
+  colreduce_kernel<MODE><<<blocks, kThreads, 0, st>>>(a, b, y, saved, ss, out, rows, C, g, act);
   return check_launch("colreduce_kernel");
 }
 
@@ -216,66 +269,123 @@ __global__ void bn_finalize_kernel(float* __restrict__ stats, const float* __res
 }
 
 // ----------------------------------------------------------------------------- BN apply
-__global__ void __launch_bounds__(kThreads)
+template <bool HAS_RES, bool RES_BN>
+__global__ void __launch_bounds__(kThreads, 2)
 bn_apply_kernel(const void* __restrict__ y, const float* __restrict__ ss, const void* __restrict__ res,
-                const float* __restrict__ rss, void* __restrict__ out, long long nvec, int C, int act) {
-  const int vpr = C >> 3;
-  for (long long vi = (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec;
-       vi += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(vi % vpr) * 8;
-    float f[8];
-    unpack8(ldg8(y, vi), f);
-    const float4 sa = *reinterpret_cast<const float4*>(ss + c0), sb = *reinterpret_cast<const float4*>(ss + c0 + 4);
-    const float4 ha = *reinterpret_cast<const float4*>(ss + C + c0), hb = *reinterpret_cast<const float4*>(ss + C + c0 + 4);
-    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-    const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                const float* __restrict__ rss, void* __restrict__ out, long long rows, int C, SlabGeom gm,
+                int act) {
+  const int vpr = gm.vpr;
+  const int tx = threadIdx.x % gm.tx_count;
+  const int ty = threadIdx.x / gm.tx_count;
+  if (tx >= vpr) return;
+  float sc[8], sh[8], rsc[8], rsh[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = f[i] * sc[i] + sh[i];
-    if (res) {
-      float r[8];
-      unpack8(ldg8(res, vi), r);
-      if (rss) {
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = ss[tx * 8 + i];
+    sh[i] = ss[C + tx * 8 + i];
+    rsc[i] = RES_BN ? rss[tx * 8 + i] : 1.f;
+    rsh[i] = RES_BN ? rss[C + tx * 8 + i] : 0.f;
+  }
+  const long long r0 = (long long)blockIdx.x * gm.rows_per_block;
+  long long r1 = r0 + gm.rows_per_block;
+  if (r1 > rows) r1 = rows;
+  for (long long r = r0 + ty; r < r1; r += (long long)gm.ty_count * UNROLL) {
+    V8 vy[UNROLL], vr[UNROLL];
+    bool ok[UNROLL];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = r[i] * rss[c0 + i] + rss[C + c0 + i];
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long rr = r + (long long)u * gm.ty_count;
+      ok[u] = rr < r1;
+      if (ok[u]) {
+        vy[u] = ldg8(y, rr * vpr + tx);
+        if (HAS_RES) vr[u] = ldg8(res, rr * vpr + tx);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += r[i];
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = act_apply(f[i], act);
-    stg8(out, vi, pack8(f));
+    for (int u = 0; u < UNROLL; ++u) {
+      if (!ok[u]) continue;
+      float f[8];
+      unpack8(vy[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = f[i] * sc[i] + sh[i];
+      if (HAS_RES) {
+        float rv[8];
+        unpack8(vr[u], rv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += RES_BN ? rv[i] * rsc[i] + rsh[i] : rv[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = act_apply(f[i], act);
+      stg8(out, (r + (long long)u * gm.ty_count) * vpr + tx, pack8(f));
+    }
   }
 }
 
 // ----------------------------------------------------------------------------- BN backward apply
-__global__ void __launch_bounds__(kThreads)
+// dy = gamma*rstd*(g - sum_g/rows - xhat*sum_gx/rows) = A*g + B*y + K per channel
+template <bool HAS_OUT, bool HAS_DRES>
+__global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_apply_kernel(const void* __restrict__ dout, const void* __restrict__ out, const void* __restrict__ y,
                     const float* __restrict__ saved, const float* __restrict__ gamma,
-                    const float* __restrict__ sums, void* __restrict__ dy, void* __restrict__ dres,
-                    long long nvec, int C, int act, float inv_rows) {
-  const int vpr = C >> 3;
-  for (long long vi = (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec;
-       vi += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(vi % vpr) * 8;
-    float g[8], fy[8];
-    unpack8(ldg8(dout, vi), g);
-    unpack8(ldg8(y, vi), fy);
-    if (act != 0) {
-      float fo[8];
-      unpack8(ldg8(out, vi), fo);
+                    const float* __restrict__ sums, const float* __restrict__ ss, void* __restrict__ dy,
+                    void* __restrict__ dres, long long rows, int C, SlabGeom gm, int act, float inv_rows) {
+  const int vpr = gm.vpr;
+  const int tx = threadIdx.x % gm.tx_count;
+  const int ty = threadIdx.x / gm.tx_count;
+  if (tx >= vpr) return;
+  float A[8], B[8], K[8], sc[8], sh[8];
+  const bool recompute_mask = !HAS_OUT && act != 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] *= act_grad(fo[i], act);
-    }
-    if (dres) stg8(dres, vi, pack8(g));
-    float d[8];
+  for (int i = 0; i < 8; ++i) {
+    const int c = tx * 8 + i;
+    const float mean = saved[c], rstd = saved[C + c];
+    const float k1 = gamma[c] * rstd;
+    const float k2 = sums[c] * inv_rows, k3 = sums[C + c] * inv_rows;
+    A[i] = k1;
+    B[i] = -k1 * k3 * rstd;
+    K[i] = -k1 * k2 + k1 * k3 * rstd * mean;
+    sc[i] = recompute_mask ? ss[c] : 0.f;
+    sh[i] = recompute_mask ? ss[C + c] : 0.f;
+  }
+  const long long r0 = (long long)blockIdx.x * gm.rows_per_block;
+  long long r1 = r0 + gm.rows_per_block;
+  if (r1 > rows) r1 = rows;
+  for (long long r = r0 + ty; r < r1; r += (long long)gm.ty_count * UNROLL) {
+    V8 vg[UNROLL], vo[UNROLL], vy[UNROLL];
+    bool ok[UNROLL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      const float mean = saved[c], rstd = saved[C + c];
-      const float xhat = (fy[i] - mean) * rstd;
-      d[i] = gamma[c] * rstd * (g[i] - sums[c] * inv_rows - xhat * sums[C + c] * inv_rows);
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long rr = r + (long long)u * gm.ty_count;
+      ok[u] = rr < r1;
+      if (ok[u]) {
+        const long long vi = rr * vpr + tx;
+        vg[u] = ldg8(dout, vi);
+        vy[u] = ldg8(y, vi);
+        if (HAS_OUT) vo[u] = ldg8(out, vi);
+      }
     }
-    stg8(dy, vi, pack8(d));
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (!ok[u]) continue;
+      const long long vi = (r + (long long)u * gm.ty_count) * vpr + tx;
+      float g[8], fy[8];
+      unpack8(vg[u], g);
+      unpack8(vy[u], fy);
+      if (HAS_OUT) {
+        float fo[8];
+        unpack8(vo[u], fo);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] *= act_grad(fo[i], act);
+      } else if (act != 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] *= act_grad(fy[i] * sc[i] + sh[i], act);
+      }
+      if (HAS_DRES) stg8(dres, vi, pack8(g));
+      float d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = A[i] * g[i] + B[i] * fy[i] + K[i];
+      stg8(dy, vi, pack8(d));
+    }
   }
 }
 
@@ -321,30 +431,37 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, float*
   }
 }
 
+// order 0: column (r*S+s)*C + c (implicit-GEMM convs); order 1: column (c*R+r)*S + s (= torch
+// layout, used by the explicit im2col of 3-channel stems / patch embeddings)
 __global__ void prep_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int K, int C,
-                                        int R, int S, int kpad) {
+                                        int R, int S, int kpad, int order) {
   const long long total = (long long)K * kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i / kpad), j = (int)(i % kpad);
     float v = 0.f;
     if (j < R * S * C) {
-      const int tap = j / C, c = j % C;
-      v = w[((long long)k * C + c) * (R * S) + tap];
+      if (order == 1) {
+        v = w[(long long)k * C * R * S + j];
+      } else {
+        const int tap = j / C, c = j % C;
+        v = w[((long long)k * C + c) * (R * S) + tap];
+      }
     }
     o[i] = __float2bfloat16_rn(v);
   }
 }
 
 __global__ void finish_conv_wgrad_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits,
-                                         int K, int C, int R, int S, int kpad, int accumulate) {
+                                         int K, int C, int R, int S, int kpad, int accumulate, int order) {
   const long long total = (long long)K * C * R * S;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int tap = (int)(i % (R * S));
     const long long kc = i / (R * S);
     const int c = (int)(kc % C), k = (int)(kc / C);
-    const long long src = (long long)k * kpad + (long long)tap * C + c;
+    const long long src = order == 1 ? (long long)k * kpad + (i - (long long)k * C * R * S)
+                                     : (long long)k * kpad + (long long)tap * C + c;
     float s = accumulate ? grad[i] : 0.f;
     for (int sp = 0; sp < splits; ++sp) s += partial[(long long)sp * K * kpad + src];
     grad[i] = s;
@@ -362,33 +479,45 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
   }
 }
 
-// one thread per (output pixel, 8-column vector) of the im2col matrix
-__global__ void stem_im2col_kernel(const float* __restrict__ x, void* __restrict__ cols, int N, int C, int H, int W,
-                                   int R, int S, int stride, int pad, int P, int Q, int kpad) {
+// Explicit im2col for 3-channel inputs (ResNet stems, ViT patch embedding).  One block owns T
+// consecutive output pixels of one output row: the (C, R, (T-1)*stride+S) input patch is staged in
+// shared memory with coalesced loads, then written out as 16-byte bf16 vectors of the row-major
+// [pixels][kpad] matrix, column (c*R+r)*S + s.
+__global__ void __launch_bounds__(kThreads)
+stem_im2col_kernel(const float* __restrict__ x, void* __restrict__ cols, int N, int C, int H, int W, int R, int S,
+                   int stride, int pad, int P, int Q, int kpad, int T) {
+  extern __shared__ float sm[];
+  const int Wt = (T - 1) * stride + S;
+  float* patch = sm;                                      // [C*R][Wt]
+  int* koff = reinterpret_cast<int*>(sm + C * R * Wt);    // [kpad] offset of column k inside `patch`
+  const int qtiles = (Q + T - 1) / T;
+  const int qt = blockIdx.x % qtiles;
+  const int p = (blockIdx.x / qtiles) % P;
+  const int n = blockIdx.x / (qtiles * P);
+  const int q0 = qt * T;
+  const int h0 = p * stride - pad, w0 = q0 * stride - pad;
+  for (int i = threadIdx.x; i < C * R * Wt; i += blockDim.x) {
+    const int wi = i % Wt, cr = i / Wt;
+    const int r = cr % R, c = cr / R;
+    const int h = h0 + r, w = w0 + wi;
+    float v = 0.f;
+    if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(x + (((long long)n * C + c) * H + h) * W + w);
+    patch[i] = v;
+  }
+  for (int k = threadIdx.x; k < kpad; k += blockDim.x) koff[k] = k < C * R * S ? (k / S) * Wt + (k % S) : -1;
+  __syncthreads();
   const int vpr = kpad >> 3;
-  const long long total = (long long)N * P * Q * vpr;
-  const int RSC = R * S * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vpr);
-    const long long m = i / vpr;
-    const int q = (int)(m % Q);
-    const int p = (int)((m / Q) % P);
-    const int n = (int)(m / ((long long)P * Q));
+  const int npix = min(T, Q - q0);
+  const long long row0 = ((long long)n * P + p) * Q + q0;
+  for (int v = threadIdx.x; v < npix * vpr; v += blockDim.x) {
+    const int pix = v / vpr, kv = v - pix * vpr;
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int j = v * 8 + e;
-      float val = 0.f;
-      if (j < RSC) {
-        const int tap = j / C, c = j - tap * C;
-        const int r = tap / S, s = tap - r * S;
-        const int h = p * stride - pad + r, w = q * stride - pad + s;
-        if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(x + (((long long)n * C + c) * H + h) * W + w);
-      }
-      f[e] = val;
+      const int o = koff[kv * 8 + e];
+      f[e] = o >= 0 ? patch[o + pix * stride] : 0.f;
     }
-    stg8(cols, i, pack8(f));
+    stg8(cols, (row0 + pix) * vpr + kv, pack8(f));
   }
 }
 
@@ -564,7 +693,7 @@ const char* saicv_last_error(void) { return saicv::last_error(); }
 
 int saicv_bn_stats(const void* y, float* stats, long long rows, int c, void* stream) {
   cudaMemsetAsync(stats, 0, sizeof(float) * 2 * c, ST);
-  return launch_colreduce<0>(y, nullptr, nullptr, nullptr, stats, rows, c, 0, ST);
+  return launch_colreduce<0>(y, nullptr, nullptr, nullptr, nullptr, stats, rows, c, 0, ST);
 }
 
 int saicv_bn_finalize(float* stats, const float* gamma, const float* beta, float* running_mean,
@@ -577,26 +706,43 @@ int saicv_bn_finalize(float* stats, const float* gamma, const float* beta, float
 
 int saicv_bn_apply(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift,
                    void* out, long long rows, int c, int act, void* stream) {
-  if (c % 8) return set_error("saicv_bn_apply: C %% 8 != 0");
-  const long long nvec = rows * (c / 8);
-  bn_apply_kernel<<<grid_for(nvec), kThreads, 0, ST>>>(y, scale_shift, res, res_scale_shift, out, nvec, c, act);
+  SlabGeom g;
+  int blocks;
+  if (!slab_geom(rows, c, UNROLL, &g, &blocks)) return 1;
+  if (res == nullptr)
+    bn_apply_kernel<false, false><<<blocks, kThreads, 0, ST>>>(y, scale_shift, res, res_scale_shift, out, rows, c, g, act);
+  else if (res_scale_shift == nullptr)
+    bn_apply_kernel<true, false><<<blocks, kThreads, 0, ST>>>(y, scale_shift, res, res_scale_shift, out, rows, c, g, act);
+  else
+    bn_apply_kernel<true, true><<<blocks, kThreads, 0, ST>>>(y, scale_shift, res, res_scale_shift, out, rows, c, g, act);
   return check_launch("bn_apply_kernel");
 }
 
-int saicv_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* saved, float* sums,
-                        long long rows, int c, int act, void* stream) {
-  if (act != 0 && out == nullptr) return set_error("saicv_bn_bwd_reduce: activated output required when act != 0");
+int saicv_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* saved,
+                        const float* scale_shift, float* sums, long long rows, int c, int act, void* stream) {
+  if (act != 0 && out == nullptr && scale_shift == nullptr)
+    return set_error("saicv_bn_bwd_reduce: need the activated output or scale_shift to form the activation mask");
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, ST);
-  return launch_colreduce<1>(dout, out, y, saved, sums, rows, c, act, ST);
+  return launch_colreduce<1>(dout, out, y, saved, scale_shift, sums, rows, c, act, ST);
 }
 
 int saicv_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* saved, const float* gamma,
-                       float* sums, void* dy, void* dres, float* dgamma, float* dbeta, long long rows, int c,
-                       int act, int accumulate, void* stream) {
-  if (c % 8) return set_error("saicv_bn_bwd_apply: C %% 8 != 0");
-  const long long nvec = rows * (c / 8);
-  bn_bwd_apply_kernel<<<grid_for(nvec), kThreads, 0, ST>>>(dout, out, y, saved, gamma, sums, dy, dres, nvec, c, act,
-                                                           1.0f / (float)rows);
+                       const float* scale_shift, float* sums, void* dy, void* dres, float* dgamma, float* dbeta,
+                       long long rows, int c, int act, int accumulate, void* stream) {
+  if (act != 0 && out == nullptr && scale_shift == nullptr)
+    return set_error("saicv_bn_bwd_apply: need the activated output or scale_shift to form the activation mask");
+  SlabGeom g;
+  int blocks;
+  if (!slab_geom(rows, c, UNROLL, &g, &blocks)) return 1;
+  const float inv_rows = 1.0f / (float)rows;
+#define BWD_APPLY(HO, HD) \
+  bn_bwd_apply_kernel<HO, HD><<<blocks, kThreads, 0, ST>>>(dout, out, y, saved, gamma, sums, scale_shift, dy, dres, rows, c, g, act, inv_rows)
+  if (out != nullptr && act != 0) {
+    if (dres) BWD_APPLY(true, true); else BWD_APPLY(true, false);
+  } else {
+    if (dres) BWD_APPLY(false, true); else BWD_APPLY(false, false);
+  }
+#undef BWD_APPLY
   if (int e = check_launch("bn_bwd_apply_kernel")) return e;
   bn_param_grad_kernel<<<(c + 127) / 128, 128, 0, ST>>>(sums, dgamma, dbeta, c, accumulate);
   return check_launch("bn_param_grad_kernel");
@@ -619,17 +765,18 @@ int saicv_reduce_partials(const float* partial, float* out, int splits, long lon
   return check_launch("reduce_partials_kernel");
 }
 
-int saicv_prep_conv_weight(const float* w, void* w_bf16, int k, int c, int r, int s, int kpad, void* stream) {
+int saicv_prep_conv_weight(const float* w, void* w_bf16, int k, int c, int r, int s, int kpad, int order,
+                           void* stream) {
   if (kpad % 8 || kpad < r * s * c) return set_error("saicv_prep_conv_weight: bad kpad %d", kpad);
   prep_conv_weight_kernel<<<grid_for((long long)k * kpad), kThreads, 0, ST>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(w_bf16), k, c, r, s, kpad);
+      w, reinterpret_cast<__nv_bfloat16*>(w_bf16), k, c, r, s, kpad, order);
   return check_launch("prep_conv_weight_kernel");
 }
 
 int saicv_finish_conv_wgrad(const float* partial, float* grad, int splits, int k, int c, int r, int s, int kpad,
-                            int accumulate, void* stream) {
+                            int accumulate, int order, void* stream) {
   finish_conv_wgrad_kernel<<<grid_for((long long)k * c * r * s), kThreads, 0, ST>>>(partial, grad, splits, k, c, r,
-                                                                                     s, kpad, accumulate);
+                                                                                     s, kpad, accumulate, order);
   return check_launch("finish_conv_wgrad_kernel");
 }
 
@@ -643,8 +790,12 @@ int saicv_stem_im2col(const float* x, void* cols, int n, int c, int h, int w, in
                       int kpad, void* stream) {
   if (kpad % 8 || kpad < r * s * c) return set_error("saicv_stem_im2col: bad kpad %d", kpad);
   const int P = (h + 2 * pad - r) / stride + 1, Q = (w + 2 * pad - s) / stride + 1;
-  stem_im2col_kernel<<<grid_for((long long)n * P * Q * (kpad / 8)), kThreads, 0, ST>>>(x, cols, n, c, h, w, r, s,
-                                                                                      stride, pad, P, Q, kpad);
+  int T = 32;  // output pixels per block; shrink until the staged patch fits in 40 KB
+  while (T > 1 && ((size_t)c * r * ((T - 1) * stride + s) * 4 + (size_t)kpad * 4) > 40 * 1024) T >>= 1;
+  const size_t smem = (size_t)c * r * ((T - 1) * stride + s) * 4 + (size_t)kpad * 4;
+  if (smem > 48 * 1024) return set_error("saicv_stem_im2col: patch of %zu bytes does not fit in shared memory", smem);
+  const long long blocks = (long long)n * P * ((Q + T - 1) / T);
+  stem_im2col_kernel<<<(unsigned)blocks, kThreads, smem, ST>>>(x, cols, n, c, h, w, r, s, stride, pad, P, Q, kpad, T);
   return check_launch("stem_im2col_kernel");
 }
 
@@ -693,7 +844,7 @@ int saicv_colsum(const void* x, float* out, long long rows, int c, int accumulat
     return check_launch("colsum_f32_kernel");
   }
   if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * c, ST);
-  return launch_colreduce<2>(x, nullptr, nullptr, nullptr, out, rows, c, 0, ST);
+  return launch_colreduce<2>(x, nullptr, nullptr, nullptr, nullptr, out, rows, c, 0, ST);
 }
 
 }  // extern "C"

@@ -141,7 +141,17 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, con
   return 0;
 }
 
-int pick_bn(int N) { return N <= 64 ? 64 : (N <= 128 ? 128 : 256); }
+// Tile width with the least padded columns (ties -> wider tile).
+int pick_bn(int N) {
+  const int cand[4] = {256, 192, 128, 64};
+  int best = 256;
+  long long best_cost = -1;
+  for (int i = 0; i < 4; ++i) {
+    const long long cost = (long long)((N + cand[i] - 1) / cand[i]) * cand[i];
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cand[i]; }
+  }
+  return best;
+}
 
 int dispatch(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, GemmParams& p,
              cudaStream_t st) {
@@ -149,6 +159,7 @@ int dispatch(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorM
   switch (bn) {
     case 64: return launch<64>(a, b, d, p, st);
     case 128: return launch<128>(a, b, d, p, st);
+    case 192: return launch<192>(a, b, d, p, st);
     default: return launch<256>(a, b, d, p, st);
   }
 }
@@ -265,8 +276,8 @@ int saicv_conv_fprop(const void* x, const void* w, void* y, const saicv_conv_sha
   return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream);
 }
 
-int saicv_conv_dgrad(const void* dy, const void* w, void* dx, const saicv_conv_shape* cs,
-                     void* stream) {
+int saicv_conv_dgrad(const void* dy, const void* w, const void* add, void* dx,
+                     const saicv_conv_shape* cs, void* stream) {
   if (!ensure_init()) return 1;
   if (cs->c % 64 || cs->k % 64 || !aligned16(dy) || !aligned16(w) || !aligned16(dx))
     return set_error("saicv_conv_dgrad: needs c%%64==0 and k%%64==0 (c=%d k=%d)", cs->c, cs->k);
@@ -285,7 +296,8 @@ int saicv_conv_dgrad(const void* dy, const void* w, void* dx, const saicv_conv_s
   p.a_mode = A_IM2COL; p.b_mode = B_MN2D; p.flip_taps = 1; p.b_cin = cs->c;
   p.g.P = cs->h; p.g.Q = cs->w; p.g.stride = 1; p.g.lc_h = lc_h; p.g.lc_w = lc_w;
   p.g.R = cs->r; p.g.S = cs->s; p.g.cchunks = cs->k / 64; p.g.n_img = cs->n;
-  p.epi_flags = 0; p.out_f32 = 0; p.out = dx; p.ldd = cs->c;
+  p.epi_flags = add ? EPI_RESID_BF16 : 0; p.resid_bf16 = add; p.out_f32 = 0; p.out = dx; p.ldd = cs->c;
+  if (add && !aligned16(add)) return set_error("saicv_conv_dgrad: unaligned `add`");
   return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream);
 }
 

@@ -23,7 +23,7 @@ namespace saicv {
 
 enum : int { A_K2D = 0, A_IM2COL = 1, A_MN2D = 2 };
 enum : int { B_K2D = 0, B_MN2D = 2, B_IM2COL = 3 };
-enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_GELU = 4, EPI_DIRECT = 8, EPI_RESID = 16 };
+enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_GELU = 4, EPI_DIRECT = 8, EPI_RESID = 16, EPI_RESID_BF16 = 32 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -64,6 +64,7 @@ struct GemmParams {
   int out_f32;         // 1: D is fp32, else bf16
   const float* bias;   // [N] or null
   const float* resid;  // fp32 [M, ldd] residual added in the epilogue (EPI_RESID) or null
+  const void* resid_bf16;  // bf16 [M, ldd] tensor added in the epilogue (EPI_RESID_BF16) or null
   void* out;           // direct-store path
   long long ldd;       // leading dimension of D in elements
   long long split_stride;  // elements between split-K partial outputs
@@ -299,6 +300,23 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (col0 + j < p.N) {
               const float4 rv = *reinterpret_cast<const float4*>(rp + j);
               f[j] += rv.x; f[j + 1] += rv.y; f[j + 2] += rv.z; f[j + 3] += rv.w;
+            }
+          }
+        }
+        if ((p.epi_flags & EPI_RESID_BF16) && row < p.M) {
+          const uint4* rp = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const __nv_bfloat16*>(p.resid_bf16) + row * p.ldd + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (col0 + 8 * j < p.N) {
+              const uint4 rv = __ldg(rp + j);
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 ab = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
+                f[8 * j + 2 * t] += ab.x;
+                f[8 * j + 2 * t + 1] += ab.y;
+              }
             }
           }
         }

@@ -93,7 +93,8 @@ class ConvBN:
             self.w_version = None
         ver = (w.data_ptr(), w._version)
         if ver != self.w_version:
-            ops.prep_conv_weight(w.detach(), self.w_bf16, self.kpad)
+            ops.prep_conv_weight(w.detach(), self.w_bf16, self.kpad,
+                                 order=ops.ORDER_CRS if self.is_stem else ops.ORDER_RSC)
             self.w_version = ver
 
     # ---- forward
@@ -150,31 +151,38 @@ class ConvBN:
 
     # ---- backward
     def bn_bwd(self, dout, tape, sink, act_out=None, want_dres=False, act=None):
-        """dout: gradient w.r.t. the activated output.  Returns (dy, dres)."""
+        """dout: gradient w.r.t. the activated output.  Returns (dy, dres).
+
+        The ReLU mask comes from `act_out` (block output, when a residual was added before the
+        activation) or, for plain conv->BN->ReLU units, is recomputed inside the kernels from
+        sign(y*scale+shift), which saves reading the activated tensor twice."""
         act = self.act if act is None else act
         y = tape['y']
-        out = act_out if act_out is not None else tape.get('out')
-        ops.bn_bwd_reduce(dout, out if act != ACT_NONE else None, y, self.saved, self.sums, act)
+        mask_src = act_out if act != ACT_NONE else None
+        ss = self.ss if (act != ACT_NONE and mask_src is None) else None
+        ops.bn_bwd_reduce(dout, mask_src, y, self.saved, self.sums, act, scale_shift=ss)
         dy = torch.empty_like(y)
         dres = torch.empty_like(y) if want_dres else None
         gbuf, gacc = sink.begin(self.bn.weight)
         bbuf, bacc = sink.begin(self.bn.bias)
         assert gacc == bacc
-        ops.bn_bwd_apply(dout, out if act != ACT_NONE else None, y, self.saved, self.bn.weight.detach(),
-                         self.sums, dy, dres, gbuf, bbuf, act, accumulate=gacc)
+        ops.bn_bwd_apply(dout, mask_src, y, self.saved, self.bn.weight.detach(), self.sums, dy, dres,
+                         gbuf, bbuf, act, accumulate=gacc, scale_shift=ss)
         sink.done(self.bn.weight, gbuf)
         sink.done(self.bn.bias, bbuf)
         return dy, dres
 
-    def conv_bwd(self, dy, tape, sink, need_dx=True):
-        """dy: gradient w.r.t. the raw conv output [n,P,Q,k].  Returns dx (NHWC bf16) or None."""
+    def conv_bwd(self, dy, tape, sink, need_dx=True, add=None):
+        """dy: gradient w.r.t. the raw conv output [n,P,Q,k].  Returns the data gradient
+        (NHWC bf16, `add` fused in when given) or None.  A 1x1 stride-2 conv returns
+        ('strided', dd) with the compact gradient dd[n,P,Q,c] that belongs at the even pixels."""
         w = self.conv.weight
         wbuf, wacc = sink.begin(w)
         n, P, Q, _ = dy.shape
         h, wd = tape['in_hw']
         if self.is_stem:
             part = ops.linear_wgrad(dy.view(-1, self.k), tape['cols'])
-            ops.finish_conv_wgrad(part, wbuf, self.kpad, accumulate=wacc)
+            ops.finish_conv_wgrad(part, wbuf, self.kpad, accumulate=wacc, order=ops.ORDER_CRS)
             sink.done(w, wbuf)
             assert not need_dx, 'the stem has no data gradient'
             return None
@@ -185,15 +193,14 @@ class ConvBN:
         if not need_dx:
             return None
         if self.stride == 1:
-            return ops.conv_dgrad(dy, self.w_bf16, cs)
+            return ops.conv_dgrad(dy, self.w_bf16, cs, add=add)
         assert self.stride == 2
         if self.r == 1:
-            dd = ops.linear_dgrad(dy.view(-1, self.k), self.w_bf16).view(n, P, Q, self.c)
-            dx = torch.zeros(n, h, wd, self.c, device=dy.device, dtype=torch.bfloat16)
-            return ops.add_strided2(dx, dd)
+            assert add is None
+            return 'strided', ops.linear_dgrad(dy.view(-1, self.k), self.w_bf16).view(n, P, Q, self.c)
         u = ops.zero_upsample2(dy, h, wd)
         cs1 = ops.make_conv_shape(n, h, wd, self.c, self.k, self.r, self.s, 1, self.pad)
-        return ops.conv_dgrad(u, self.w_bf16, cs1)
+        return ops.conv_dgrad(u, self.w_bf16, cs1, add=add)
 
 
 class ResidualBlockRT:
@@ -230,17 +237,23 @@ class ResidualBlockRT:
         last, tl = self.units[-1], tapes[-1]
         out = tl['out']
         # g = dout * relu'(out) flows to both the last BN and the shortcut
-        dy, g = last.bn_bwd(dout, tl, sink, want_dres=(self.down is None))
-        d_short = None
+        dy, g = last.bn_bwd(dout, tl, sink, act_out=out, want_dres=(self.down is None))
+        shortcut, strided = g, None
         if self.down is not None:
             td = tape['d']
             dyd, _ = self.down.bn_bwd(dout, td, sink, act_out=out, act=ACT_RELU)
-            d_short = self.down.conv_bwd(dyd, td, sink)
-        dx = last.conv_bwd(dy, tl, sink)
-        for u, t in zip(reversed(self.units[:-1]), reversed(tapes[:-1])):
+            shortcut = self.down.conv_bwd(dyd, td, sink)
+            if isinstance(shortcut, tuple):
+                strided, shortcut = shortcut[1], None
+        dx = last.conv_bwd(dy, tl, sink, add=shortcut if len(self.units) == 1 else None)
+        inner = list(zip(self.units[:-1], tapes[:-1]))
+        for i in range(len(inner) - 1, -1, -1):
+            u, t = inner[i]
             dy, _ = u.bn_bwd(dx, t, sink)
-            dx = u.conv_bwd(dy, t, sink)
-        ops.add_bf16(dx, d_short if d_short is not None else g)
+            # the first conv of the block produces the block-input gradient: fuse the shortcut add
+            dx = u.conv_bwd(dy, t, sink, add=shortcut if i == 0 else None)
+        if strided is not None:
+            ops.add_strided2(dx, strided)
         return dx
 
 

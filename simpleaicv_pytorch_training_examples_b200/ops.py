@@ -88,11 +88,12 @@ def conv_fprop(x, w, cs, out=None, flags=0):
     return out
 
 
-def conv_dgrad(dy, w, cs, out=None):
-    """dy: [n, h, w, k] (zero-upsampled for strided convs); cs.stride must be 1."""
+def conv_dgrad(dy, w, cs, out=None, add=None):
+    """dy: [n, h, w, k] (zero-upsampled for strided convs); cs.stride must be 1.
+    add: optional bf16 [n, h, w, c] tensor summed into the result in the GEMM epilogue."""
     if out is None:
         out = torch.empty(cs.n, cs.h, cs.w, cs.c, device=dy.device, dtype=torch.bfloat16)
-    _lib.call('saicv_conv_dgrad', _p(dy), _p(w), _p(out), ctypes.byref(cs), _stream())
+    _lib.call('saicv_conv_dgrad', _p(dy), _p(w), _p(add), _p(out), ctypes.byref(cs), _stream())
     return out
 
 
@@ -107,16 +108,19 @@ def conv_wgrad(dy, x, cs, partial=None):
     return partial
 
 
-def prep_conv_weight(w_f32, out, kpad):
+ORDER_RSC, ORDER_CRS = 0, 1  # K ordering of weight matrices: implicit GEMM / explicit im2col
+
+
+def prep_conv_weight(w_f32, out, kpad, order=ORDER_RSC):
     k, c, r, s = w_f32.shape
-    _lib.call('saicv_prep_conv_weight', _p(w_f32), _p(out), k, c, r, s, kpad, _stream())
+    _lib.call('saicv_prep_conv_weight', _p(w_f32), _p(out), k, c, r, s, kpad, order, _stream())
     return out
 
 
-def finish_conv_wgrad(partial, grad, kpad, accumulate=False):
+def finish_conv_wgrad(partial, grad, kpad, accumulate=False, order=ORDER_RSC):
     k, c, r, s = grad.shape
     _lib.call('saicv_finish_conv_wgrad', _p(partial), _p(grad), partial.shape[0], k, c, r, s, kpad,
-              int(accumulate), _stream())
+              int(accumulate), order, _stream())
     return grad
 
 
@@ -178,16 +182,19 @@ def bn_apply(y, scale_shift, out, act, res=None, res_scale_shift=None):
     return out
 
 
-def bn_bwd_reduce(dout, out, y, saved, sums, act):
+def bn_bwd_reduce(dout, out, y, saved, sums, act, scale_shift=None):
+    """`out` None + scale_shift given: the activation mask is recomputed from y."""
     c = y.shape[-1]
-    _lib.call('saicv_bn_bwd_reduce', _p(dout), _p(out), _p(y), _p(saved), _p(sums), y.numel() // c, c,
-              act, _stream())
+    _lib.call('saicv_bn_bwd_reduce', _p(dout), _p(out), _p(y), _p(saved), _p(scale_shift), _p(sums),
+              y.numel() // c, c, act, _stream())
 
 
-def bn_bwd_apply(dout, out, y, saved, gamma, sums, dy, dres, dgamma, dbeta, act, accumulate=False):
+def bn_bwd_apply(dout, out, y, saved, gamma, sums, dy, dres, dgamma, dbeta, act, accumulate=False,
+                 scale_shift=None):
     c = y.shape[-1]
-    _lib.call('saicv_bn_bwd_apply', _p(dout), _p(out), _p(y), _p(saved), _p(gamma), _p(sums), _p(dy),
-              _p(dres), _p(dgamma), _p(dbeta), y.numel() // c, c, act, int(accumulate), _stream())
+    _lib.call('saicv_bn_bwd_apply', _p(dout), _p(out), _p(y), _p(saved), _p(gamma), _p(scale_shift),
+              _p(sums), _p(dy), _p(dres), _p(dgamma), _p(dbeta), y.numel() // c, c, act,
+              int(accumulate), _stream())
 
 
 def add_bf16(a, b):

@@ -117,7 +117,9 @@ def test_conv_dgrad(n, h, w, c, k, r, stride, pad):
     dy = dy_nchw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
     ref = torch.nn.grad.conv2d_input(x_nchw.shape, wt, dy_nchw, stride=stride, padding=pad).permute(0, 2, 3, 1)
     if stride == 1:
-        dx = ops.conv_dgrad(dy, wb, cs)
+        add = _bf(n, h, w, c, seed=23)
+        dx = ops.conv_dgrad(dy, wb, cs, add=add)
+        ref = ref + add.float()
     elif r == 1:
         # 1x1 stride 2: compact GEMM + strided scatter-add
         dd = ops.linear_dgrad(dy.view(-1, k), wb).view(n, P, Q, c)
@@ -143,27 +145,28 @@ def test_conv_wgrad(n, h, w, c, k, r, stride, pad):
     _close(dw, ref, 1e-3, 1e-3, f'conv_wgrad splits={part.shape[0]}')
 
 
-def test_stem_im2col_matches_conv():
+@pytest.mark.parametrize('n,c,h,w,k,r,stride,pad,kpad', [(4, 3, 32, 32, 64, 7, 2, 3, 192), (3, 3, 37, 41, 64, 3, 1, 1, 64),
+                                                       (2, 3, 64, 64, 128, 16, 16, 0, 768), (2, 3, 224, 224, 64, 7, 2, 3, 192)])
+def test_stem_im2col_matches_conv(n, c, h, w, k, r, stride, pad, kpad):
     ops = _ops()
-    n, c, h, w, k, r, stride, pad = 4, 3, 32, 32, 64, 7, 2, 3
     x = _bf(n, c, h, w, seed=11).float()
     wt = _bf(k, c, r, r, scale=0.1, seed=12).float()
-    kpad = 192
     cols = ops.stem_im2col(x, r, r, stride, pad, kpad)
     wb = torch.empty(k, kpad, device='cuda', dtype=torch.bfloat16)
-    ops.prep_conv_weight(wt.contiguous(), wb, kpad)
+    ops.prep_conv_weight(wt.contiguous(), wb, kpad, order=ops.ORDER_CRS)
     y = ops.linear_fwd(cols, wb)
     P = ops.conv_out_size(h, pad, r, stride)
     ref = F.conv2d(x, wt, stride=stride, padding=pad).permute(0, 2, 3, 1).reshape(-1, k)
     _close(y, ref, 1e-2, 1e-2, 'stem conv via im2col')
     # weight gradient through the same matrix
-    dy = _bf(n * P * P, k, scale=0.05, seed=13)
+    P2 = ops.conv_out_size(w, pad, r, stride)
+    dy = _bf(n * P * P2, k, scale=0.05, seed=13)
     part = ops.linear_wgrad(dy, cols)
     dwp = torch.empty(1, k, kpad, device='cuda')
     ops.reduce_partials(part, dwp[0])
     dw = torch.empty(k, c, r, r, device='cuda')
-    ops.finish_conv_wgrad(dwp, dw, kpad)
-    ref_dw = torch.nn.grad.conv2d_weight(x, wt.shape, dy.float().view(n, P, P, k).permute(0, 3, 1, 2), stride=stride, padding=pad)
+    ops.finish_conv_wgrad(dwp, dw, kpad, order=ops.ORDER_CRS)
+    ref_dw = torch.nn.grad.conv2d_weight(x, wt.shape, dy.float().view(n, P, P2, k).permute(0, 3, 1, 2), stride=stride, padding=pad)
     _close(dw, ref_dw, 1e-3, 1e-3, 'stem wgrad')
 
 
@@ -204,6 +207,16 @@ def test_bn_forward_backward(rows, c):
     _close(dgamma, g.grad, 2e-2, 2e-2 * scale, 'dgamma')
     _close(dres, resf.grad, 1e-2, 1e-2, 'dres', max_bad_frac=1e-3)
     _close(dy, yf.grad, 2e-2, 2e-2, 'bn dy', max_bad_frac=1e-3)
+    # plain conv->BN->ReLU unit: the mask is recomputed from y inside the kernels (no `out` read)
+    out2 = torch.empty_like(y)
+    ops.bn_apply(y, ss, out2, 1)
+    yf2 = y.float().requires_grad_(True)
+    ref2 = F.relu(F.batch_norm(yf2, None, None, gamma, beta, True, 0.1, 1e-5))
+    ref2.backward(dout.float())
+    dy2 = torch.empty_like(y)
+    ops.bn_bwd_reduce(dout, None, y, saved, sums, 1, scale_shift=ss)
+    ops.bn_bwd_apply(dout, None, y, saved, gamma, sums, dy2, None, dgamma, dbeta, 1, scale_shift=ss)
+    _close(dy2, yf2.grad, 2e-2, 2e-2, 'bn dy (recomputed mask)', max_bad_frac=1e-3)
 
 
 def test_maxpool_avgpool():
