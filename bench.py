@@ -182,7 +182,7 @@ def _cs(a):
 def describe(name, a):
     """(key, algorithmic flops, algorithmic bytes) of one C-ABI call from its arguments."""
     if name in ('saicv_conv_fprop', 'saicv_conv_dgrad', 'saicv_conv_wgrad'):
-        cs = _cs(a[3])
+        cs = next(_cs(v) for v in a if hasattr(v, '_obj'))
         st = cs.stride
         P = (cs.h + 2 * cs.pad - cs.r) // st + 1
         Q = (cs.w + 2 * cs.pad - cs.s) // st + 1

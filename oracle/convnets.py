@@ -142,18 +142,30 @@ def _conv_bn(sd, prefix, x, k, stride, training, emu):
     return y
 
 
-def forward(sd, x, arch, training=True, emulate_bf16=False):
+def _keep(trace, key, t):
+    """Records an intermediate tensor (and asks autograd to keep its gradient) for the
+    stage-by-stage parity tests."""
+    if trace is not None:
+        if t.requires_grad:
+            t.retain_grad()
+        trace[key] = t
+    return t
+
+
+def forward(sd, x, arch, training=True, emulate_bf16=False, trace=None):
     """Logits of `arch` for the NCHW fp32 batch x; running statistics in `sd` are updated in
-    place when training (like nn.BatchNorm2d)."""
+    place when training (like nn.BatchNorm2d).  `trace` (a dict) receives the stage boundary
+    tensors: 'stem_out', 'pool_out', 'block{i}_out', 'logits'."""
     emu = emulate_bf16
     block, nums, cifar = ARCHS[arch]
     specs, _ = _cba_specs(arch)
     spec = {p: (k, s) for p, _, _, k, s in specs}
     if emu:
         x = x.bfloat16().float()
-    x = _act_store(F.relu(_conv_bn(sd, 'conv1', x, *spec['conv1'], training, emu)), emu)
+    x = _keep(trace, 'stem_out', _act_store(F.relu(_conv_bn(sd, 'conv1', x, *spec['conv1'], training, emu)), emu))
     if not cifar:
-        x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+        x = _keep(trace, 'pool_out', F.max_pool2d(x, kernel_size=3, stride=2, padding=1))
+    bidx = 0
     for li in range(4):
         for bi in range(nums[li]):
             p = f'layer{li + 1}.{bi}'
@@ -167,9 +179,10 @@ def forward(sd, x, arch, training=True, emulate_bf16=False):
             if f'{p}.downsample_conv' in spec:
                 k, s = spec[f'{p}.downsample_conv']
                 inp = _conv_bn(sd, f'{p}.downsample_conv', inp, k, s, training, emu)
-            x = _act_store(F.relu(x + inp), emu)
+            x = _keep(trace, f'block{bidx}_out', _act_store(F.relu(x + inp), emu))
+            bidx += 1
     x = _act_store(F.adaptive_avg_pool2d(x, (1, 1)).flatten(1), emu)
     z = F.linear(x, _w_operand(sd['fc.weight'], emu))
     if emu:
         z = _RoundGrad.apply(z)
-    return z + sd['fc.bias']
+    return _keep(trace, 'logits', z + sd['fc.bias'])

@@ -21,14 +21,14 @@ def ce_loss(logits, labels):
     return torch.sum(-labels * F.log_softmax(logits, dim=-1), dim=-1).mean()
 
 
-def loss_and_grads(sd, x, labels, arch, emulate_bf16=False):
+def loss_and_grads(sd, x, labels, arch, emulate_bf16=False, trace=None):
     """Returns (logits, loss, {param name: grad}); BN running stats in sd are updated.
     emulate_bf16: evaluate with the B200 path's bf16 storage points (convnets.forward)."""
     names = convnets.param_names(sd)
     for n in names:
         sd[n].requires_grad_(True)
         sd[n].grad = None
-    logits = convnets.forward(sd, x, arch, training=True, emulate_bf16=emulate_bf16)
+    logits = convnets.forward(sd, x, arch, training=True, emulate_bf16=emulate_bf16, trace=trace)
     loss = ce_loss(logits, labels)
     loss.backward()
     grads = {n: sd[n].grad.detach().clone() for n in names}

@@ -245,13 +245,14 @@ class ResidualBlockRT:
             shortcut = self.down.conv_bwd(dyd, td, sink)
             if isinstance(shortcut, tuple):
                 strided, shortcut = shortcut[1], None
-        dx = last.conv_bwd(dy, tl, sink, add=shortcut if len(self.units) == 1 else None)
-        inner = list(zip(self.units[:-1], tapes[:-1]))
-        for i in range(len(inner) - 1, -1, -1):
-            u, t = inner[i]
+        dx = last.conv_bwd(dy, tl, sink)
+        for u, t in zip(reversed(self.units[:-1]), reversed(tapes[:-1])):
             dy, _ = u.bn_bwd(dx, t, sink)
-            # the first conv of the block produces the block-input gradient: fuse the shortcut add
-            dx = u.conv_bwd(dy, t, sink, add=shortcut if i == 0 else None)
+            dx = u.conv_bwd(dy, t, sink)
+        # TODO(perf): fuse this add into the dgrad epilogue once the epilogue loads its residual
+        # tile with TMA (the per-thread row-strided loads of EPI_RESID_BF16 are slower than this pass)
+        if shortcut is not None:
+            ops.add_bf16(dx, shortcut)
         if strided is not None:
             ops.add_strided2(dx, strided)
         return dx
@@ -296,17 +297,16 @@ class ResNetRT:
             self.fc_version = ver
         self.fc_b_pad[:w.shape[0]].copy_(self.fc.bias.detach())
 
-    def forward(self, x, training, keep_tape):
-        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
-        x = x.contiguous()
-        self.prep()
-        tape = {'stem': {}, 'blocks': [dict() for _ in self.blocks]}
+    # The network is run as three stages (stem / residual blocks / head) so that tests can drive
+    # each stage with the oracle's tensors (tests/test_resnet_gpu.py, teacher-forced parity).
+    def stem_forward(self, x, tape, training):
         a = self.stem.forward(x, tape['stem'], training)
         if self.has_maxpool:
             tape['pool_in_hw'] = (a.shape[1], a.shape[2])
             a, tape['argmax'] = ops.maxpool3x3s2_fwd(a)
-        for b, t in zip(self.blocks, tape['blocks']):
-            a = b.forward(a, t, training)
+        return a
+
+    def head_forward(self, a, tape):
         tape['feat_hw'] = (a.shape[1], a.shape[2])
         pooled = ops.avgpool_fwd(a)
         tape['pooled'] = pooled
@@ -314,13 +314,23 @@ class ResNetRT:
         logits = ops.linear_fwd(pooled, self.fc_w_bf16, bias=self.fc_b_pad, out_f32=True)
         if logits.shape[1] != ncls:
             logits = logits[:, :ncls].contiguous()
+        return logits
+
+    def forward(self, x, training, keep_tape):
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+        x = x.contiguous()
+        self.prep()
+        tape = {'stem': {}, 'blocks': [dict() for _ in self.blocks]}
+        a = self.stem_forward(x, tape, training)
+        for b, t in zip(self.blocks, tape['blocks']):
+            a = b.forward(a, t, training)
+        logits = self.head_forward(a, tape)
         self.tape = tape if keep_tape else None
         return logits
 
-    def backward(self, dlogits):
-        tape, sink = self.tape, self.sink
-        assert tape is not None, 'backward called without a training forward'
-        self.tape = None
+    def head_backward(self, dlogits, tape):
+        """dlogits fp32 [B, num_classes] -> gradient w.r.t. the last feature map (NHWC bf16)."""
+        sink = self.sink
         ncls, feat = self.fc.weight.shape
         npad = self.fc_w_bf16.shape[0]
         dlogits = dlogits.contiguous().float()
@@ -343,14 +353,23 @@ class ResNetRT:
         sink.done(self.fc.weight, wbuf)
         dpooled = ops.linear_dgrad(dl, self.fc_w_bf16)
         h, w = tape['feat_hw']
-        da = ops.avgpool_bwd(dpooled, h, w)
-        for b, t in zip(reversed(self.blocks), reversed(tape['blocks'])):
-            da = b.backward(da, t, sink)
+        return ops.avgpool_bwd(dpooled, h, w)
+
+    def stem_backward(self, da, tape):
         if self.has_maxpool:
             ph, pw = tape['pool_in_hw']
             da = ops.maxpool3x3s2_bwd(da, tape['argmax'], ph, pw)
-        dy, _ = self.stem.bn_bwd(da, tape['stem'], sink)
-        self.stem.conv_bwd(dy, tape['stem'], sink, need_dx=False)
+        dy, _ = self.stem.bn_bwd(da, tape['stem'], self.sink)
+        self.stem.conv_bwd(dy, tape['stem'], self.sink, need_dx=False)
+
+    def backward(self, dlogits):
+        tape, sink = self.tape, self.sink
+        assert tape is not None, 'backward called without a training forward'
+        self.tape = None
+        da = self.head_backward(dlogits, tape)
+        for b, t in zip(reversed(self.blocks), reversed(tape['blocks'])):
+            da = b.backward(da, t, sink)
+        self.stem_backward(da, tape)
         if sink.on_backward_end is not None:
             sink.on_backward_end()
 
