@@ -26,9 +26,10 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-METRIC = 'images/sec (ResNet-50 224x224 training step, whole job)'
-R50_FWD_FLOPS = 8.178e9      # per image, forward; a training step is 3x
-R50_ALGO_BYTES = 130e6       # per image per step, bf16 activations written once / read once (8d)
+METRICS = {'resnet50': 'images/sec (ResNet-50 224x224 training step, whole job)',
+           'vit_base_patch16': 'images/sec (ViT-B/16 224x224 training step, whole job)'}
+FWD_FLOPS = {'resnet50': 8.178e9, 'vit_base_patch16': 35.13e9}   # per image forward; a step is 3x
+ALGO_BYTES = {'resnet50': 130e6, 'vit_base_patch16': 3 * 65e6}  # per image per step, activations once each way (8d)
 
 
 def _peaks():
@@ -92,20 +93,23 @@ def build_optimizer(model, lr=0.1, momentum=0.9, weight_decay=1e-4):
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_oracle_images_per_sec(batch, steps, threads):
+def cpu_oracle_images_per_sec(model, batch, steps, threads):
     """The reference's CPU path (its model code restated by oracle/) on this box's host cores."""
-    from oracle import convnets, train_step
+    from oracle import convnets, train_step, vit
     torch.set_num_threads(threads)
-    sd = convnets.init_state('resnet50', 1000, 0)
     g = torch.Generator().manual_seed(0)
     x = torch.randn(batch, 3, 224, 224, generator=g)
     y = torch.randint(0, 1000, (batch,), generator=g)
+    sd = convnets.init_state('resnet50', 1000, 0) if model == 'resnet50' else vit.init_state(model, 1000, 0)
     buf = {}
     times = []
     for i in range(steps + 1):
         t0 = time.perf_counter()
-        _, _, grads = train_step.loss_and_grads(sd, x, y, 'resnet50')
-        train_step.sgd_step(sd, grads, buf, 0.1)
+        if model == 'resnet50':
+            _, _, grads = train_step.loss_and_grads(sd, x, y, 'resnet50')
+        else:
+            _, _, grads = vit.loss_and_grads(sd, x, y, model, global_pool=True)
+        train_step.sgd_step(sd, grads, buf, 0.1)  # the CPU cost of the parameter update is negligible either way
         if i > 0:
             times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
@@ -119,12 +123,12 @@ def run_reference(args, rank):
     cores = os.cpu_count() or 1
     batch = 16
     steps = max(1, min(args.steps, 3))
-    ips, dt = cpu_oracle_images_per_sec(batch, steps, cores)
+    ips, dt = cpu_oracle_images_per_sec(args.model, batch, steps, cores)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
+        'impl': 'reference', 'metric': METRICS[args.model], 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
         'warmup': 1, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'ResNet-50 224x224 training step (CELoss, SGD), reference model code on CPU',
+        'config': {'workload': f'{args.model} 224x224 training step, reference model code on CPU',
                    'per_step_batch': batch},
         'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                          'sample': f'{steps} timed steps of batch {batch} (1 warm-up), fp32, torch {torch.__version__} CPU'},
@@ -213,14 +217,31 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     B = args.batch
     torch.manual_seed(0)
-    model = backbones.resnet50(num_classes=1000).to(dev).train()
-    crit = losses.CELoss().to(dev)
-    opt = build_optimizer(model)
-    net = B200DataParallel(model) if world > 1 else model
-
     g = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
-    y_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
+    if args.model == 'resnet50':
+        model = backbones.resnet50(num_classes=1000).to(dev).train()
+        crit = losses.CELoss().to(dev)
+        opt = build_optimizer(model)
+        y_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
+        workload = 'ResNet-50 224x224 bs256/GPU training step (fwd+CELoss+bwd+grad all-reduce+SGD)'
+    else:
+        # BASELINE configs[2] / SURVEY.md 8d C3: vit_base_patch16(global_pool, drop_path 0.1), soft labels,
+        # OneHotLabelCELoss, AdamW(5e-4, wd .05) with layer-wise lr decay .65
+        from simpleaicv_pytorch_training_examples_b200.tools import utils as tutils
+        model = backbones.vit_base_patch16(image_size=224, num_classes=1000, drop_path_prob=0.1, global_pool=True).to(dev).train()
+        crit = losses.OneHotLabelCELoss().to(dev)
+
+        class _Cfg:
+            optimizer = ('AdamW', {'lr': 5e-4, 'global_weight_decay': False, 'weight_decay': 0.05,
+                                   'no_weight_decay_layer_name_list': ['position_encoding', 'cls_token'],
+                                   'lr_layer_decay': 0.65, 'lr_layer_decay_block': model.blocks, 'block_name': 'blocks'})
+        opt, _ = tutils.build_optimizer(_Cfg, model)
+        lab = torch.randint(0, 1000, (B,), generator=g)
+        one_hot = torch.nn.functional.one_hot(lab, 1000).float() * 0.9 + 0.1 / 1000
+        y_host = (0.5 * one_hot + 0.5 * one_hot.roll(1, 0)).pin_memory()
+        workload = 'ViT-B/16 224x224 bs256/GPU training step (fwd+OneHotLabelCELoss+bwd+grad all-reduce+AdamW)'
+    net = B200DataParallel(model) if world > 1 else model
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
     def step(x, y):
@@ -304,8 +325,8 @@ def run_b200(args, rank, world, local_rank):
         gemm_ms = sum(v['ms'] for v in gemm.values())
         all_ms = sum(v['ms'] for v in table.values())
         roof['gemm_share_of_step'] = gemm_ms / all_ms if all_ms else None
-        roof['step_tensor_tflops'] = 3 * R50_FWD_FLOPS * B / (ms_step / 1e3) / 1e12
-        roof['step_hbm_gbs_algorithmic'] = R50_ALGO_BYTES * B / (ms_step / 1e3) / 1e9
+        roof['step_tensor_tflops'] = 3 * FWD_FLOPS[args.model] * B / (ms_step / 1e3) / 1e12
+        roof['step_hbm_gbs_algorithmic'] = ALGO_BYTES[args.model] * B / (ms_step / 1e3) / 1e9
         if args.dump_ops:
             rows = sorted(table.items(), key=lambda kv: -kv[1]['ms'])
             with open(args.dump_ops, 'w') as f:
@@ -316,22 +337,22 @@ def run_b200(args, rank, world, local_rank):
                             f"{v['flops'] / s / 1e12 if s else 0:.1f},{v['bytes'] / s / 1e9 if s else 0:.1f}\n")
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            ips, dt = cpu_oracle_images_per_sec(8, 2, cores)
+            ips, dt = cpu_oracle_images_per_sec(args.model, 8, 2, cores)
             cpu_base = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                        'sample': f'2 timed steps of batch 8 (1 warm-up) of the same ResNet-50 step, fp32 oracle, {dt:.2f} s/step'}
+                        'sample': f'2 timed steps of batch 8 (1 warm-up) of the same {args.model} step, fp32 oracle, {dt:.2f} s/step'}
 
     if rank == 0:
         line = {
-            'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
+            'metric': METRICS[args.model], 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic',
-            'config': {'workload': 'ResNet-50 224x224 bs256/GPU training step (fwd+CELoss+bwd+grad all-reduce+SGD)',
+            'config': {'workload': workload,
                        'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': f'dp{world}',
                        'l2_policy': 'inputs+activations (>10 GB/step) far exceed the 126 MB L2; no explicit flush',
                        'images_per_sec_per_gpu': value / world},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'ms_per_step': e2e_ms,
-                    'h2d_bytes_per_step': (x_host.numel() * 4 + y_host.numel() * 8) * world, 'd2h_bytes_per_step': 4 * world},
+                    'h2d_bytes_per_step': (x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()) * world, 'd2h_bytes_per_step': 4 * world},
             'gpu_launches': int(launches),
             'roofline': roof,
             'cpu_baseline': cpu_base,
@@ -346,6 +367,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='per-GPU batch (BASELINE config: 256)')
+    ap.add_argument('--model', default='resnet50', choices=['resnet50', 'vit_base_patch16'],
+                    help='resnet50 = BASELINE configs[1] (default, the headline); vit_base_patch16 = configs[2]')
     ap.add_argument('--dump-ops', default=None, help='write the per-op timing table (csv) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -94,14 +94,18 @@ int saicv_add_strided2(void* dx, const void* dd, int n, int p, int q, int h, int
                        void* stream);
 
 /* ---- BatchNorm2d (training) + ReLU + residual (resnet.py:40-42,152-153) ------------------- */
-/* per-channel sum / sum of squares of y[rows][c] (bf16) into stats[2][c] (fp32; zeroed by
- * the call itself on `stream` before the reduction). */
-int saicv_bn_stats(const void* y, float* stats, long long rows, int c, void* stream);
-/* mean/var from stats -> scale_shift[2][c], saved[2][c] = (mean, rstd); running stats updated
- * with `momentum` and the unbiased variance exactly like nn.BatchNorm2d; stats zeroed. */
-int saicv_bn_finalize(float* stats, const float* gamma, const float* beta, float* running_mean,
-                      float* running_var, float* scale_shift, float* saved, long long rows, int c,
-                      float eps, float momentum, void* stream);
+/* Column reductions are deterministic (no atomics): every block writes one row of partial sums
+ * into a caller-provided workspace `partials` of SAICV_BN_PARTIAL_ROWS * 2 * c floats, folded in a
+ * fixed order by the next call. */
+#define SAICV_BN_PARTIAL_ROWS 296
+/* per-channel partial sum / sum of squares of y[rows][c] (bf16) -> partials. */
+int saicv_bn_stats(const void* y, float* partials, long long rows, int c, void* stream);
+/* folds `partials` (from saicv_bn_stats with the same rows, c) -> mean/var -> scale_shift[2][c],
+ * saved[2][c] = (mean, rstd); running stats updated with `momentum` and the unbiased variance
+ * exactly like nn.BatchNorm2d (running_* may be NULL). */
+int saicv_bn_finalize(const float* partials, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float* scale_shift, float* saved,
+                      long long rows, int c, float eps, float momentum, void* stream);
 /* out = act(y*scale+shift + res) ; res optional, itself optionally batch-normalised with
  * res_scale_shift (downsample branch).  act: 0 none, 1 ReLU, 2 LeakyReLU(0.1). */
 int saicv_bn_apply(const void* y, const float* scale_shift, const void* res,
@@ -111,10 +115,10 @@ int saicv_bn_apply(const void* y, const float* scale_shift, const void* res,
  * (xhat from y, saved mean/rstd).  The activation mask comes from `out` (activated output) when
  * it is non-NULL; otherwise, for a unit without residual input, it is recomputed from
  * sign(y*scale+shift) using `scale_shift` (saves reading `out`).  Both may be NULL when act == 0.
- * sums is zeroed by the call itself on `stream`. */
+ * `partials`: workspace as above; `sums[2][c]` receives the folded result. */
 int saicv_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* saved,
-                        const float* scale_shift, float* sums, long long rows, int c, int act,
-                        void* stream);
+                        const float* scale_shift, float* partials, float* sums, long long rows,
+                        int c, int act, void* stream);
 /* dy = gamma*rstd*(g - sum_g/rows - xhat*sum_gx/rows) bf16; writes dgamma/dbeta (fp32, (+)=)
  * and optionally dres = g (gradient flowing into the residual input). */
 int saicv_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* saved,
@@ -132,9 +136,42 @@ int saicv_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int 
 int saicv_avgpool_fwd(const void* x, void* y, int n, int hw, int c, void* stream);
 int saicv_avgpool_bwd(const void* dy, void* dx, int n, int hw, int c, void* stream);
 /* column sums of a bf16 (or fp32 when is_f32) [rows][c] matrix into fp32 out[c] ((+)= when
- * accumulate): bias gradients. */
-int saicv_colsum(const void* x, float* out, long long rows, int c, int accumulate, int is_f32,
-                 void* stream);
+ * accumulate): bias gradients.  `partials`: SAICV_BN_PARTIAL_ROWS * c floats (unused for fp32). */
+int saicv_colsum(const void* x, float* partials, float* out, long long rows, int c, int accumulate,
+                 int is_f32, void* stream);
+
+/* ---- ViT blocks (SimpleAICV/classification/backbones/vit.py) --------------------------------- */
+/* nn.LayerNorm(eps=1e-6) (vit.py:147,151,225): x fp32 [rows][c] -> y bf16; stats[2][rows] =
+ * (mean, rstd) kept for the backward.  c in {128, 256, 768, 1024, 1280}. */
+int saicv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y,
+                        float* stats, long long rows, int c, float eps, void* stream);
+/* dx (fp32) = dres + LN'(dy) with dres the residual-stream gradient (may be NULL); optional bf16
+ * copy of dx for the next GEMM; dgamma/dbeta (+)= column reductions (zeroed first unless
+ * accumulate). */
+int saicv_layernorm_bwd(const void* dy, const float* x, const float* gamma, const float* stats,
+                        const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                        long long rows, int c, int accumulate, void* stream);
+/* nn.GELU() exact erf (vit.py:87-89): h = gelu(u); du = dh * gelu'(u); bf16, n % 8 == 0. */
+int saicv_gelu_fwd(const void* u, void* h, long long n, void* stream);
+int saicv_gelu_bwd(const void* dh, const void* u, void* du, long long n, void* stream);
+/* x[b,0] = cls + pos[0]; x[b,1+i] = patch[b*np+i] + pos[1+i] (vit.py:242-243); all fp32. */
+int saicv_vit_assemble_tokens(const float* patch, const float* cls, const float* pos, float* x,
+                              int b, int np, int c, void* stream);
+/* dpos (+)= sum_b dx[b]; dcls (+)= sum_b dx[b,0]; dpatch[b*np+i] = bf16(dx[b,1+i]). */
+int saicv_vit_assemble_tokens_bwd(const float* dx, float* dpos, float* dcls, void* dpatch, int b,
+                                  int np, int c, int accumulate, void* stream);
+/* pooled[b] = mean of tokens 1..l-1 (mean_pool, vit.py:252-255) or token 0 (vit.py:257-258). */
+int saicv_token_pool_fwd(const float* x, float* pooled, int b, int l, int c, int mean_pool,
+                         void* stream);
+int saicv_token_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int b, int l, int c,
+                         int mean_pool, void* stream);
+/* MultiHeadAttention core (vit.py:66-76): qkv bf16 [b][l][3][h][d] -> out bf16 [b][l][h*d] =
+ * softmax(q k^T * scale) v, fused (the l x l matrix is never written); lse[b][h][l] (log2 domain)
+ * is kept for the backward.  d == 64, l <= 256. */
+int saicv_attention_fwd(const void* qkv, void* out, float* lse, int b, int l, int h, int d,
+                        float scale, void* stream);
+int saicv_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                        void* dqkv, int b, int l, int h, int d, float scale, void* stream);
 
 #ifdef __cplusplus
 }

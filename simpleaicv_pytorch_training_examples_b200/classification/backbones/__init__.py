@@ -2,3 +2,4 @@
 SimpleAICV/classification/backbones/__init__.py) executing on libsaicv_b200.so."""
 from .resnet import *  # noqa: F401,F403
 from .resnetforcifar import *  # noqa: F401,F403
+from .vit import *  # noqa: F401,F403

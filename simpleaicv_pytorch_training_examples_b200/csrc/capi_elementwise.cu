@@ -91,6 +91,7 @@ constexpr int UNROLL = 4;
 struct SlabGeom {
   int vpr, tx_count, ty_count;
   long long rows_per_block;
+  int ldv;  // row stride in 16-byte vectors (== vpr unless a column chunk of a wider matrix is reduced)
 };
 
 // MODE 0: sum x, sum x^2 (BN forward statistics)
@@ -98,7 +99,7 @@ struct SlabGeom {
 // MODE 2: sum x only (bias gradients)
 // Activation mask source for MODE 1: `b` (activated output) when non-null, else recomputed
 // from y with scale/shift `ss` (out = act(y*scale+shift) has the sign of y*scale+shift).
-template <int MODE>
+template <int MODE, int UNR>
 __global__ void __launch_bounds__(kThreads, 2)
 colreduce_kernel(const void* __restrict__ a, const void* __restrict__ b, const void* __restrict__ y,
                  const float* __restrict__ saved, const float* __restrict__ ss, float* __restrict__ out,
@@ -126,15 +127,15 @@ colreduce_kernel(const void* __restrict__ a, const void* __restrict__ b, const v
         sh[i] = recompute_mask ? ss[C + tx * 8 + i] : 0.f;
       }
     }
-    for (long long r = r0 + ty; r < r1; r += (long long)ty_count * UNROLL) {
-      V8 va[UNROLL], vb[UNROLL], vy[UNROLL];
-      bool ok[UNROLL];
+    for (long long r = r0 + ty; r < r1; r += (long long)ty_count * UNR) {
+      V8 va[UNR], vb[UNR], vy[UNR];
+      bool ok[UNR];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
+      for (int u = 0; u < UNR; ++u) {
         const long long rr = r + (long long)u * ty_count;
         ok[u] = rr < r1;
         if (ok[u]) {
-          const long long vi = rr * vpr + tx;
+          const long long vi = rr * gm.ldv + tx;
           va[u] = ldg8(a, vi);
           if (MODE == 1) {
             vy[u] = ldg8(y, vi);
@@ -143,7 +144,7 @@ colreduce_kernel(const void* __restrict__ a, const void* __restrict__ b, const v
         }
       }
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
+      for (int u = 0; u < UNR; ++u) {
         if (!ok[u]) continue;
         float fa[8];
         unpack8(va[u], fa);
@@ -185,50 +186,85 @@ colreduce_kernel(const void* __restrict__ a, const void* __restrict__ b, const v
     red[threadIdx.x][8 + i] = s1[i];
   }
   __syncthreads();
-  // threads of row ty == 0 fold the partials of the other rows sharing their channel vector
-  if (ty == 0 && tx < vpr) {
-    for (int t = 1; t < ty_count; ++t) {
+  // tree-fold the ty rows that share a channel vector
+  for (int half = ty_count >> 1; half > 0; half >>= 1) {
+    if (ty < half) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s0[i] += red[t * gm.tx_count + tx][i];
-        s1[i] += red[t * gm.tx_count + tx][8 + i];
-      }
+      for (int i = 0; i < 16; ++i) red[threadIdx.x][i] += red[threadIdx.x + half * gm.tx_count][i];
     }
+    __syncthreads();
+  }
+  // deterministic: one partial row per block, folded later by fold_partials / bn_finalize
+  if (ty == 0 && tx < vpr) {
+    float* prow = out + (long long)blockIdx.x * (MODE == 2 ? C : 2 * C);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(out + tx * 8 + i, s0[i]);
-      if (MODE != 2) atomicAdd(out + C + tx * 8 + i, s1[i]);
+      prow[tx * 8 + i] = red[threadIdx.x][i];
+      if (MODE != 2) prow[C + tx * 8 + i] = red[threadIdx.x][8 + i];
     }
   }
 }
 
-bool slab_geom(long long rows, int C, int min_rows_per_thread, SlabGeom* g, int* blocks) {
+// out[j] (+)= sum_b partial[b][j]: 32 columns x 8 row groups per block
+__global__ void fold_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblk, int ncols,
+                                     int accumulate) {
+  __shared__ float sm[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), grp = threadIdx.x >> 5;
+  float s = 0.f;
+  if (col < ncols)
+    for (int b = grp; b < nblk; b += 8) s += partial[(long long)b * ncols + col];
+  sm[grp][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (grp == 0 && col < ncols) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += sm[g][threadIdx.x];
+    out[col] = accumulate ? out[col] + t : t;
+  }
+}
+
+constexpr int kMaxPartials = SAICV_BN_PARTIAL_ROWS;  // 2 blocks per SM
+
+bool slab_geom(long long rows, int C, int unroll, SlabGeom* g, int* blocks, int max_blocks = 148 * 8) {
+  const int min_rows_per_thread = unroll;
   if (C % 8 || C > 2048) {
     set_error("BatchNorm / column kernels need C %% 8 == 0 and C <= 2048 (C=%d)", C);
     return false;
   }
   g->vpr = C / 8;
+  g->ldv = C / 8;
   g->tx_count = next_pow2(g->vpr) > kThreads ? kThreads : next_pow2(g->vpr);
   g->ty_count = kThreads / g->tx_count;
   long long b = (rows + (long long)g->ty_count * min_rows_per_thread - 1) / ((long long)g->ty_count * min_rows_per_thread);
-  if (b > 148 * 8) b = 148 * 8;
+  if (b > max_blocks) b = max_blocks;
   if (b < 1) b = 1;
   g->rows_per_block = (rows + b - 1) / b;
   // keep slabs a multiple of ty_count*UNROLL rows so only the last block has a ragged tail
-  const long long q = (long long)g->ty_count * UNROLL;
+  const long long q = (long long)g->ty_count * unroll;
   g->rows_per_block = (g->rows_per_block + q - 1) / q * q;
   *blocks = (int)((rows + g->rows_per_block - 1) / g->rows_per_block);
   return true;
 }
 
+// Writes `*nblk` partial rows into `partials` ([kMaxPartials][2C] or [..][C] for MODE 2).
 template <int MODE>
 int launch_colreduce(const void* a, const void* b, const void* y, const float* saved, const float* ss,
-                     float* out, long long rows, int C, int act, cudaStream_t st) {
+                     float* partials, long long rows, int C, int act, int* nblk, cudaStream_t st) {
   SlabGeom g;
-  int blocks;
-  if (!slab_geom(rows, C, 2 * UNROLL, &g, &blocks)) return 1;
-  colreduce_kernel<MODE><<<blocks, kThreads, 0, st>>>(a, b, y, saved, ss, out, rows, C, g, act);
+  constexpr int UNR = MODE == 1 ? 4 : 8;  // independent 16-byte loads in flight per tensor per thread
+  if (!slab_geom(rows, C, UNR, &g, nblk, kMaxPartials)) return 1;
+  colreduce_kernel<MODE, UNR><<<*nblk, kThreads, 0, st>>>(a, b, y, saved, ss, partials, rows, C, g, act);
   return check_launch("colreduce_kernel");
+}
+int partial_rows(long long rows, int C) {  // must mirror launch_colreduce<0>
+  SlabGeom g;
+  int n = 0;
+  slab_geom(rows, C, 8, &g, &n, kMaxPartials);
+  return n;
+}
+int fold(const float* partials, float* out, int nblk, int ncols, int accumulate, cudaStream_t st) {
+  fold_partials_kernel<<<(ncols + 31) / 32, 256, 0, st>>>(partials, out, nblk, ncols, accumulate);
+  return check_launch("fold_partials_kernel");
 }
 
 // fp32 column sums (fc bias gradient from fp32 dlogits): small, one thread per column
@@ -242,16 +278,34 @@ __global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict
 }
 
 // ----------------------------------------------------------------------------- BN finalize
-__global__ void bn_finalize_kernel(float* __restrict__ stats, const float* __restrict__ gamma,
+// Folds the per-block partial sums (deterministic order) and finalises 32 channels per block.
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblk, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ rmean,
                                    float* __restrict__ rvar, float* __restrict__ ss,
                                    float* __restrict__ saved, long long rows, int C, float eps,
                                    float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float sm[2][8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C)
+    for (int b = grp; b < nblk; b += 8) {
+      s0 += partials[(long long)b * 2 * C + c];
+      s1 += partials[(long long)b * 2 * C + C + c];
+    }
+  sm[0][grp][lane] = s0;
+  sm[1][grp][lane] = s1;
+  __syncthreads();
+  if (grp != 0 || c >= C) return;
+  s0 = s1 = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    s0 += sm[0][g][lane];
+    s1 += sm[1][g][lane];
+  }
   const float inv_n = 1.0f / (float)rows;
-  const float mean = stats[c] * inv_n;
-  float var = stats[C + c] * inv_n - mean * mean;
+  const float mean = s0 * inv_n;
+  float var = s1 * inv_n - mean * mean;
   var = fmaxf(var, 0.f);
   const float rstd = rsqrtf(var + eps);
   const float sc = gamma[c] * rstd;
@@ -264,8 +318,6 @@ __global__ void bn_finalize_kernel(float* __restrict__ stats, const float* __res
     rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
     rvar[c] = (1.f - momentum) * rvar[c] + momentum * unbiased;
   }
-  stats[c] = 0.f;
-  stats[C + c] = 0.f;
 }
 
 // ----------------------------------------------------------------------------- BN apply
@@ -691,16 +743,16 @@ int saicv_version(void) { return 100; }
 long long saicv_launch_count(void) { return saicv::launch_count(); }
 const char* saicv_last_error(void) { return saicv::last_error(); }
 
-int saicv_bn_stats(const void* y, float* stats, long long rows, int c, void* stream) {
-  cudaMemsetAsync(stats, 0, sizeof(float) * 2 * c, ST);
-  return launch_colreduce<0>(y, nullptr, nullptr, nullptr, nullptr, stats, rows, c, 0, ST);
+int saicv_bn_stats(const void* y, float* partials, long long rows, int c, void* stream) {
+  int nblk;
+  return launch_colreduce<0>(y, nullptr, nullptr, nullptr, nullptr, partials, rows, c, 0, &nblk, ST);
 }
 
-int saicv_bn_finalize(float* stats, const float* gamma, const float* beta, float* running_mean,
+int saicv_bn_finalize(const float* partials, const float* gamma, const float* beta, float* running_mean,
                       float* running_var, float* scale_shift, float* saved, long long rows, int c,
                       float eps, float momentum, void* stream) {
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, ST>>>(stats, gamma, beta, running_mean, running_var, scale_shift,
-                                                       saved, rows, c, eps, momentum);
+  bn_finalize_kernel<<<(c + 31) / 32, 256, 0, ST>>>(partials, partial_rows(rows, c), gamma, beta, running_mean,
+                                                    running_var, scale_shift, saved, rows, c, eps, momentum);
   return check_launch("bn_finalize_kernel");
 }
 
@@ -719,11 +771,13 @@ int saicv_bn_apply(const void* y, const float* scale_shift, const void* res, con
 }
 
 int saicv_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* saved,
-                        const float* scale_shift, float* sums, long long rows, int c, int act, void* stream) {
+                        const float* scale_shift, float* partials, float* sums, long long rows, int c, int act,
+                        void* stream) {
   if (act != 0 && out == nullptr && scale_shift == nullptr)
     return set_error("saicv_bn_bwd_reduce: need the activated output or scale_shift to form the activation mask");
-  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, ST);
-  return launch_colreduce<1>(dout, out, y, saved, scale_shift, sums, rows, c, act, ST);
+  int nblk;
+  if (int e = launch_colreduce<1>(dout, out, y, saved, scale_shift, partials, rows, c, act, &nblk, ST)) return e;
+  return fold(partials, sums, nblk, 2 * c, 0, ST);
 }
 
 int saicv_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* saved, const float* gamma,
@@ -838,13 +892,26 @@ int saicv_avgpool_bwd(const void* dy, void* dx, int n, int hw, int c, void* stre
   return check_launch("avgpool_bwd_kernel");
 }
 
-int saicv_colsum(const void* x, float* out, long long rows, int c, int accumulate, int is_f32, void* stream) {
+int saicv_colsum(const void* x, float* partials, float* out, long long rows, int c, int accumulate, int is_f32,
+                 void* stream) {
   if (is_f32) {
     colsum_f32_kernel<<<(c + 127) / 128, 128, 0, ST>>>(reinterpret_cast<const float*>(x), out, rows, c, accumulate);
     return check_launch("colsum_f32_kernel");
   }
-  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * c, ST);
-  return launch_colreduce<2>(x, nullptr, nullptr, nullptr, nullptr, out, rows, c, 0, ST);
+  if (c % 8) return set_error("saicv_colsum: C %% 8 != 0");
+  // columns are reduced in chunks of <= 2048 (the slab kernels keep one 16-byte vector per thread)
+  for (int c0 = 0; c0 < c; c0 += 2048) {
+    const int cw = c - c0 < 2048 ? c - c0 : 2048;
+    SlabGeom g;
+    int nblk;
+    if (!slab_geom(rows, cw, 8, &g, &nblk, kMaxPartials)) return 1;
+    g.ldv = c / 8;
+    colreduce_kernel<2, 8><<<nblk, kThreads, 0, ST>>>(reinterpret_cast<const __nv_bfloat16*>(x) + c0, nullptr, nullptr, nullptr,
+                                                   nullptr, partials, rows, cw, g, 0);
+    if (int e = check_launch("colreduce_kernel")) return e;
+    if (int e = fold(partials, out + c0, nblk, cw, accumulate, ST)) return e;
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -75,7 +75,6 @@ class ConvBN:
         self.kpad = _round_up(r * s * c, 64) if self.is_stem else r * s * c
         self.w_bf16 = None
         self.w_version = None
-        self.stats = None
         self.ss = None
         self.saved = None
         self.sums = None
@@ -86,7 +85,6 @@ class ConvBN:
         if self.w_bf16 is None or self.w_bf16.device != w.device:
             dev = w.device
             self.w_bf16 = torch.empty(self.k, self.kpad, device=dev, dtype=torch.bfloat16)
-            self.stats = torch.zeros(2, self.k, device=dev)
             self.ss = torch.empty(2, self.k, device=dev)
             self.saved = torch.empty(2, self.k, device=dev)
             self.sums = torch.zeros(2, self.k, device=dev)
@@ -126,8 +124,8 @@ class ConvBN:
         rows = y.numel() // self.k
         if training or not bn.track_running_stats:
             momentum = bn.momentum if bn.momentum is not None else 0.1
-            ops.bn_stats(y, self.stats)
-            ops.bn_finalize(self.stats, bn.weight.detach(), bn.bias.detach(),
+            partials = ops.bn_stats(y)
+            ops.bn_finalize(partials, bn.weight.detach(), bn.bias.detach(),
                             bn.running_mean if bn.track_running_stats else None,
                             bn.running_var if bn.track_running_stats else None,
                             self.ss, self.saved, rows, bn.eps, momentum)

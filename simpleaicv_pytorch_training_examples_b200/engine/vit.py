@@ -1,0 +1,275 @@
+"""Forward/backward runtime of the ViT classifiers on libsaicv_b200.so.
+
+Per block (SimpleAICV/classification/backbones/vit.py:159-161, pre-LN):
+    x = x + drop_path(proj(attention(qkv(LN1(x)))))        x: fp32 residual stream [B*L, C]
+    x = x + drop_path(fc2(gelu(fc1(LN2(x)))))
+Every Linear is one launch of the tcgen05 GEMM engine (csrc/gemm_sm100.cuh): forward with the
+bias (+ fp32 residual) fused in the epilogue, data gradient with W consumed MN-major, weight
+gradient with both operands MN-major and split-K.  LayerNorm, GELU, token assembly / pooling and
+the fused attention are in csrc/capi_vit.cu.  dtype flow = the reference under autocast
+(SURVEY.md Appendix C): fp32 residual stream / LN statistics / softmax, bf16 GEMM operands.
+
+DropPath (vit.py:102-135): the per-sample Bernoulli(keep)/keep scale is drawn with torch on the
+device (one [B] tensor per branch) and applied to the branch output and to its gradient.
+"""
+import torch
+
+from .. import ops
+from .convnet import GradSink
+
+
+class _Linear:
+    """bf16 operand copy + forward / backward of one nn.Linear."""
+
+    def __init__(self, mod):
+        self.mod = mod
+        self.w_bf16 = None
+        self.version = None
+
+    def prep(self):
+        w = self.mod.weight
+        ver = (w.data_ptr(), w._version)
+        if self.w_bf16 is None or ver != self.version:
+            if self.w_bf16 is None or self.w_bf16.device != w.device:
+                npad = (w.shape[0] + 7) // 8 * 8
+                self.w_bf16 = torch.zeros(npad, w.shape[1], device=w.device, dtype=torch.bfloat16)
+                self.b_pad = torch.zeros(npad, device=w.device)
+            ops.cast_bf16(w.detach(), self.w_bf16[:w.shape[0]])
+            self.version = ver
+        self.b_pad[:w.shape[0]].copy_(self.mod.bias.detach())
+
+    def fwd(self, x, resid=None, out_f32=False):
+        return ops.linear_fwd(x, self.w_bf16, bias=self.b_pad, resid=resid, out_f32=out_f32)
+
+    def bwd(self, dy, x, sink, need_dx=True):
+        """dy bf16 [M, N], x bf16 [M, K]: writes dW, db through the sink, returns dx bf16."""
+        w, b = self.mod.weight, self.mod.bias
+        n = w.shape[0]
+        wbuf, wacc = sink.begin(w)
+        part = ops.linear_wgrad(dy, x)
+        if part.shape[1] == n:
+            ops.reduce_partials(part, wbuf, accumulate=wacc)
+        else:  # padded class dimension
+            tmp = torch.empty(part.shape[1], part.shape[2], device=dy.device)
+            ops.reduce_partials(part, tmp)
+            wbuf.copy_(tmp[:n] + (wbuf if wacc else 0))
+        sink.done(w, wbuf)
+        bbuf, bacc = sink.begin(b)
+        if dy.shape[1] == n:
+            ops.colsum(dy, bbuf, accumulate=bacc)
+        else:
+            full = torch.empty(dy.shape[1], device=dy.device)
+            ops.colsum(dy, full)
+            bbuf.copy_(full[:n] + (bbuf if bacc else 0))
+        sink.done(b, bbuf)
+        return ops.linear_dgrad(dy, self.w_bf16) if need_dx else None
+
+
+class _Block:
+
+    def __init__(self, blk):
+        self.blk = blk
+        self.qkv, self.proj = _Linear(blk.attn.qkv), _Linear(blk.attn.proj)
+        self.fc1, self.fc2 = _Linear(blk.mlp.fc1), _Linear(blk.mlp.fc2)
+        self.heads = blk.attn.head_nums
+        self.scale = blk.attn.scale
+        self.drop_path = getattr(blk.drop_path, 'drop_path_prob', 0.)
+
+    def linears(self):
+        return [self.qkv, self.proj, self.fc1, self.fc2]
+
+    def _path_scale(self, b, l, training, dev):
+        if not training or self.drop_path == 0.:
+            return None
+        keep = 1. - self.drop_path
+        s = torch.empty(b, device=dev).bernoulli_(keep)
+        if keep > 0.:
+            s.div_(keep)
+        return s
+
+    def forward(self, x, t, b, l, training):
+        """x: fp32 [B*L, C] -> fp32 [B*L, C]"""
+        blk, c = self.blk, x.shape[1]
+        d = c // self.heads
+        t['x_in'] = x
+        t['ln1'], t['st1'] = ops.layernorm_fwd(x, blk.norm1.weight.detach(), blk.norm1.bias.detach(), blk.norm1.eps)
+        t['qkv'] = self.qkv.fwd(t['ln1'])
+        t['att'], t['lse'] = ops.attention_fwd(t['qkv'], b, l, self.heads, d, self.scale)
+        s1 = t['s1'] = self._path_scale(b, l, training, x.device)
+        if s1 is None:
+            x = self.proj.fwd(t['att'], resid=x, out_f32=True)
+        else:
+            branch = self.proj.fwd(t['att'], out_f32=True)
+            x = x + (branch.view(b, l, c) * s1.view(b, 1, 1)).view(b * l, c)
+        t['x_mid'] = x
+        t['ln2'], t['st2'] = ops.layernorm_fwd(x, blk.norm2.weight.detach(), blk.norm2.bias.detach(), blk.norm2.eps)
+        t['u'] = self.fc1.fwd(t['ln2'])
+        t['h'] = ops.gelu_fwd(t['u'])
+        s2 = t['s2'] = self._path_scale(b, l, training, x.device)
+        if s2 is None:
+            x = self.fc2.fwd(t['h'], resid=x, out_f32=True)
+        else:
+            branch = self.fc2.fwd(t['h'], out_f32=True)
+            x = x + (branch.view(b, l, c) * s2.view(b, 1, 1)).view(b * l, c)
+        return x
+
+    def _scaled(self, dxb, s, b, l):
+        if s is None:
+            return dxb
+        c = dxb.shape[1]
+        return (dxb.view(b, l, c).float() * s.view(b, 1, 1)).to(torch.bfloat16).view(b * l, c)
+
+    def _ln_bwd(self, norm, dy, x, stats, dres, sink):
+        gbuf, gacc = sink.begin(norm.weight)
+        bbuf, bacc = sink.begin(norm.bias)
+        dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+        dx = ops.layernorm_bwd(dy, x, norm.weight.detach(), stats, gbuf, bbuf, dres=dres, dx_bf16=dxb, accumulate=gacc)
+        sink.done(norm.weight, gbuf)
+        sink.done(norm.bias, bbuf)
+        return dx, dxb
+
+    def backward(self, dx, dxb, t, b, l, sink):
+        """dx fp32 / dxb bf16: gradient w.r.t. the block output.  Returns (dx_in fp32, bf16 copy)."""
+        blk = self.blk
+        d = dx.shape[1] // self.heads
+        # ---- MLP branch
+        dyb = self._scaled(dxb, t['s2'], b, l)
+        dh = self.fc2.bwd(dyb, t['h'], sink)
+        du = ops.gelu_bwd(dh, t['u'])
+        dln2 = self.fc1.bwd(du, t['ln2'], sink)
+        dx, dxb = self._ln_bwd(blk.norm2, dln2, t['x_mid'], t['st2'], dx, sink)
+        # ---- attention branch
+        dyb = self._scaled(dxb, t['s1'], b, l)
+        datt = self.proj.bwd(dyb, t['att'], sink)
+        dqkv = ops.attention_bwd(t['qkv'], t['att'], datt, t['lse'], b, l, self.heads, d, self.scale)
+        dln1 = self.qkv.bwd(dqkv, t['ln1'], sink)
+        return self._ln_bwd(blk.norm1, dln1, t['x_in'], t['st1'], dx, sink)
+
+
+class ViTRT:
+    """Whole-network runtime (vit.py:239-262)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.blocks = [_Block(b) for b in model.blocks]
+        self.fc = _Linear(model.fc)
+        self.sink = GradSink()
+        self.tape = None
+        self.pw_bf16 = None
+        self.pw_version = None
+
+    def prep(self):
+        for b in self.blocks:
+            for lin in b.linears():
+                lin.prep()
+        self.fc.prep()
+        w = self.model.patch_embed.proj.weight
+        ver = (w.data_ptr(), w._version)
+        if self.pw_bf16 is None or ver != self.pw_version:
+            k = w.shape[1] * w.shape[2] * w.shape[3]
+            self.kpad = (k + 63) // 64 * 64
+            if self.pw_bf16 is None:
+                self.pw_bf16 = torch.empty(w.shape[0], self.kpad, device=w.device, dtype=torch.bfloat16)
+            ops.prep_conv_weight(w.detach(), self.pw_bf16, self.kpad, order=ops.ORDER_CRS)
+            self.pw_version = ver
+
+    # ---- stages (driven separately by the teacher-forced parity tests)
+    def embed_forward(self, x, tape):
+        m = self.model
+        b = x.shape[0]
+        p = m.patch_size
+        cols = ops.stem_im2col(x, p, p, p, 0, self.kpad)
+        tape['cols'] = cols
+        patch = ops.linear_fwd(cols, self.pw_bf16, bias=m.patch_embed.proj.bias.detach(), out_f32=True)
+        np_ = cols.shape[0] // b
+        c = m.embedding_planes
+        tokens = ops.vit_assemble_tokens(patch, m.cls_token.detach().view(-1), m.pos_embed.detach().view(-1, c), b, np_, c)
+        tape['b'], tape['l'] = b, np_ + 1
+        return tokens.view(b * (np_ + 1), c)
+
+    def head_forward(self, x, tape):
+        m = self.model
+        b, l, c = tape['b'], tape['l'], m.embedding_planes
+        pooled = ops.token_pool_fwd(x.view(b, l, c), m.global_pool)
+        tape['pooled'] = pooled
+        tape['lnf'], tape['stf'] = ops.layernorm_fwd(pooled, m.norm.weight.detach(), m.norm.bias.detach(), m.norm.eps)
+        logits = self.fc.fwd(tape['lnf'], out_f32=True)
+        ncls = m.fc.weight.shape[0]
+        return logits if logits.shape[1] == ncls else logits[:, :ncls].contiguous()
+
+    def forward(self, x, training, keep_tape):
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+        self.prep()
+        tape = {'blocks': [dict() for _ in self.blocks]}
+        h = self.embed_forward(x.contiguous(), tape)
+        for blk, t in zip(self.blocks, tape['blocks']):
+            h = blk.forward(h, t, tape['b'], tape['l'], training)
+        logits = self.head_forward(h, tape)
+        self.tape = tape if keep_tape else None
+        return logits
+
+    def head_backward(self, dlogits, tape):
+        m, sink = self.model, self.sink
+        b, l, c = tape['b'], tape['l'], m.embedding_planes
+        ncls = m.fc.weight.shape[0]
+        npad = self.fc.w_bf16.shape[0]
+        dl = torch.zeros(b, npad, device=dlogits.device, dtype=torch.bfloat16)
+        dl[:, :ncls] = dlogits.to(torch.bfloat16)
+        # fc bias gradient from the fp32 dlogits
+        bbuf, bacc = sink.begin(m.fc.bias)
+        ops.colsum(dlogits.contiguous().float(), bbuf, accumulate=bacc)
+        dlnf = self._fc_bwd_nobias(dl, tape['lnf'])
+        sink.done(m.fc.bias, bbuf)
+        gbuf, gacc = sink.begin(m.norm.weight)
+        nbuf, nacc = sink.begin(m.norm.bias)
+        dpooled = ops.layernorm_bwd(dlnf, tape['pooled'], m.norm.weight.detach(), tape['stf'], gbuf, nbuf, accumulate=gacc)
+        sink.done(m.norm.weight, gbuf)
+        sink.done(m.norm.bias, nbuf)
+        dxb = torch.empty(b * l, c, device=dl.device, dtype=torch.bfloat16)
+        dx = ops.token_pool_bwd(dpooled, l, m.global_pool, dx_bf16=dxb.view(b, l, c))
+        return dx.view(b * l, c), dxb
+
+    def _fc_bwd_nobias(self, dl, x):
+        m, sink = self.model, self.sink
+        w = m.fc.weight
+        n = w.shape[0]
+        wbuf, wacc = sink.begin(w)
+        part = ops.linear_wgrad(dl, x)
+        if part.shape[1] == n:
+            ops.reduce_partials(part, wbuf, accumulate=wacc)
+        else:
+            tmp = torch.empty(part.shape[1], part.shape[2], device=dl.device)
+            ops.reduce_partials(part, tmp)
+            wbuf.copy_(tmp[:n] + (wbuf if wacc else 0))
+        sink.done(w, wbuf)
+        return ops.linear_dgrad(dl, self.fc.w_bf16)
+
+    def embed_backward(self, dx, tape):
+        m, sink = self.model, self.sink
+        b, l, c = tape['b'], tape['l'], m.embedding_planes
+        pbuf, pacc = sink.begin(m.pos_embed)
+        cbuf, cacc = sink.begin(m.cls_token)
+        assert pacc == cacc
+        dpatch = torch.empty(b * (l - 1), c, device=dx.device, dtype=torch.bfloat16)
+        ops.vit_assemble_tokens_bwd(dx.view(b, l, c), pbuf, cbuf, dpatch, accumulate=pacc)
+        sink.done(m.pos_embed, pbuf)
+        sink.done(m.cls_token, cbuf)
+        w, bias = m.patch_embed.proj.weight, m.patch_embed.proj.bias
+        wbuf, wacc = sink.begin(w)
+        part = ops.linear_wgrad(dpatch, tape['cols'])
+        ops.finish_conv_wgrad(part, wbuf, self.kpad, accumulate=wacc, order=ops.ORDER_CRS)
+        sink.done(w, wbuf)
+        bbuf, bacc = sink.begin(bias)
+        ops.colsum(dpatch, bbuf, accumulate=bacc)
+        sink.done(bias, bbuf)
+
+    def backward(self, dlogits):
+        tape, sink = self.tape, self.sink
+        assert tape is not None, 'backward called without a training forward'
+        self.tape = None
+        dx, dxb = self.head_backward(dlogits, tape)
+        for blk, t in zip(reversed(self.blocks), reversed(tape['blocks'])):
+            dx, dxb = blk.backward(dx, dxb, t, tape['b'], tape['l'], sink)
+        self.embed_backward(dx, tape)
+        if sink.on_backward_end is not None:
+            sink.on_backward_end()

@@ -164,9 +164,26 @@ def add_strided2(dx, dd):
 
 
 # ----------------------------------------------------------------------------- batch norm
-def bn_stats(y, stats):
+_WS = {}
+
+
+def partial_ws(device, ncols):
+    """Workspace for the deterministic column reductions (SAICV_BN_PARTIAL_ROWS x ncols floats),
+    one per (device, width); safe to share because every use is ordered on the stream."""
+    key = (device, ncols)
+    ws = _WS.get(key)
+    if ws is None:
+        ws = _WS[key] = torch.empty(_lib.BN_PARTIAL_ROWS * ncols, device=device, dtype=torch.float32)
+    return ws
+
+
+def bn_stats(y, partials=None):
+    """Returns the partial-sum workspace to hand to bn_finalize (same rows, c)."""
     c = y.shape[-1]
-    _lib.call('saicv_bn_stats', _p(y), _p(stats), y.numel() // c, c, _stream())
+    if partials is None:
+        partials = partial_ws(y.device, 2 * c)
+    _lib.call('saicv_bn_stats', _p(y), _p(partials), y.numel() // c, c, _stream())
+    return partials
 
 
 def bn_finalize(stats, gamma, beta, rmean, rvar, scale_shift, saved, rows, eps, momentum):
@@ -185,8 +202,8 @@ def bn_apply(y, scale_shift, out, act, res=None, res_scale_shift=None):
 def bn_bwd_reduce(dout, out, y, saved, sums, act, scale_shift=None):
     """`out` None + scale_shift given: the activation mask is recomputed from y."""
     c = y.shape[-1]
-    _lib.call('saicv_bn_bwd_reduce', _p(dout), _p(out), _p(y), _p(saved), _p(scale_shift), _p(sums),
-              y.numel() // c, c, act, _stream())
+    _lib.call('saicv_bn_bwd_reduce', _p(dout), _p(out), _p(y), _p(saved), _p(scale_shift),
+              _p(partial_ws(y.device, 2 * c)), _p(sums), y.numel() // c, c, act, _stream())
 
 
 def bn_bwd_apply(dout, out, y, saved, gamma, sums, dy, dres, dgamma, dbeta, act, accumulate=False,
@@ -240,6 +257,89 @@ def avgpool_bwd(dy, h, w, out=None):
 
 def colsum(x, out, accumulate=False):
     c = x.shape[-1]
-    _lib.call('saicv_colsum', _p(x), _p(out), x.numel() // c, c, int(accumulate),
-              int(x.dtype == torch.float32), _stream())
+    is_f32 = x.dtype == torch.float32
+    ws = None if is_f32 else partial_ws(x.device, c)
+    _lib.call('saicv_colsum', _p(x), _p(ws), _p(out), x.numel() // c, c, int(accumulate), int(is_f32), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------- ViT blocks
+def layernorm_fwd(x, gamma, beta, eps, out=None, stats=None):
+    rows, c = x.numel() // x.shape[-1], x.shape[-1]
+    assert x.dtype == torch.float32
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    if stats is None:
+        stats = torch.empty(2, rows, device=x.device, dtype=torch.float32)
+    _lib.call('saicv_layernorm_fwd', _p(x), _p(gamma), _p(beta), _p(out), _p(stats), rows, c, eps, _stream())
+    return out, stats
+
+
+def layernorm_bwd(dy, x, gamma, stats, dgamma, dbeta, dres=None, dx=None, dx_bf16=None, accumulate=False):
+    rows, c = x.numel() // x.shape[-1], x.shape[-1]
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.float32
+    if dx is None:
+        dx = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _lib.call('saicv_layernorm_bwd', _p(dy), _p(x), _p(gamma), _p(stats), _p(dres), _p(dx), _p(dx_bf16),
+              _p(dgamma), _p(dbeta), rows, c, int(accumulate), _stream())
+    return dx
+
+
+def gelu_fwd(u, out=None):
+    if out is None:
+        out = torch.empty_like(u)
+    _lib.call('saicv_gelu_fwd', _p(u), _p(out), u.numel(), _stream())
+    return out
+
+
+def gelu_bwd(dh, u, out=None):
+    if out is None:
+        out = torch.empty_like(u)
+    _lib.call('saicv_gelu_bwd', _p(dh), _p(u), _p(out), u.numel(), _stream())
+    return out
+
+
+def vit_assemble_tokens(patch, cls, pos, b, np_, c, out=None):
+    if out is None:
+        out = torch.empty(b, np_ + 1, c, device=patch.device, dtype=torch.float32)
+    _lib.call('saicv_vit_assemble_tokens', _p(patch), _p(cls), _p(pos), _p(out), b, np_, c, _stream())
+    return out
+
+
+def vit_assemble_tokens_bwd(dx, dpos, dcls, dpatch, accumulate=False):
+    b, l, c = dx.shape
+    _lib.call('saicv_vit_assemble_tokens_bwd', _p(dx), _p(dpos), _p(dcls), _p(dpatch), b, l - 1, c,
+              int(accumulate), _stream())
+    return dpatch
+
+
+def token_pool_fwd(x, mean_pool, out=None):
+    b, l, c = x.shape
+    if out is None:
+        out = torch.empty(b, c, device=x.device, dtype=torch.float32)
+    _lib.call('saicv_token_pool_fwd', _p(x), _p(out), b, l, c, int(mean_pool), _stream())
+    return out
+
+
+def token_pool_bwd(dpooled, l, mean_pool, dx=None, dx_bf16=None):
+    b, c = dpooled.shape
+    if dx is None:
+        dx = torch.empty(b, l, c, device=dpooled.device, dtype=torch.float32)
+    _lib.call('saicv_token_pool_bwd', _p(dpooled), _p(dx), _p(dx_bf16), b, l, c, int(mean_pool), _stream())
+    return dx
+
+
+def attention_fwd(qkv, b, l, h, d, scale, out=None, lse=None):
+    if out is None:
+        out = torch.empty(b * l, h * d, device=qkv.device, dtype=torch.bfloat16)
+    if lse is None:
+        lse = torch.empty(b, h, l, device=qkv.device, dtype=torch.float32)
+    _lib.call('saicv_attention_fwd', _p(qkv), _p(out), _p(lse), b, l, h, d, scale, _stream())
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, b, l, h, d, scale, dqkv=None):
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    _lib.call('saicv_attention_bwd', _p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), b, l, h, d, scale, _stream())
+    return dqkv

@@ -181,8 +181,8 @@ def test_bn_forward_backward(rows, c):
     rmean, rvar = torch.zeros(c, device='cuda'), torch.ones(c, device='cuda')
     stats = torch.zeros(2, c, device='cuda')
     ss, saved = torch.empty(2, c, device='cuda'), torch.empty(2, c, device='cuda')
-    ops.bn_stats(y, stats)
-    ops.bn_finalize(stats, gamma, beta, rmean, rvar, ss, saved, rows, 1e-5, 0.1)
+    part = ops.bn_stats(y)
+    ops.bn_finalize(part, gamma, beta, rmean, rvar, ss, saved, rows, 1e-5, 0.1)
     out = torch.empty_like(y)
     ops.bn_apply(y, ss, out, 1, res=res)
     # torch reference (fp32 on the same bf16 inputs)
