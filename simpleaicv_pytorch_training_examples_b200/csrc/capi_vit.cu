@@ -253,6 +253,17 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, const 
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a));
 }
 
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
 constexpr int HD = 64;      // head dim
 constexpr int LDS = 72;     // smem row stride (bf16): 144 B keeps 32-bit fragment loads and ldmatrix conflict free
 
@@ -266,75 +277,79 @@ __device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat
     *reinterpret_cast<uint4*>(dst + r * LDS + v * 8) = val;
   }
 }
-__device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], const __nv_bfloat16* s, int row0, int g, int t) {
+// A fragments (16 rows x 64 k) of the row-major tile starting at row0: one ldmatrix.x4 per k16 step
+// (matrices: rows 0-7 / 8-15 x k 0-7 / 8-15 = a0, a1, a2, a3).
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], const __nv_bfloat16* s, int row0, int lane) {
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    a[kk][0] = *reinterpret_cast<const uint32_t*>(s + (row0 + g) * LDS + kk * 16 + 2 * t);
-    a[kk][1] = *reinterpret_cast<const uint32_t*>(s + (row0 + g + 8) * LDS + kk * 16 + 2 * t);
-    a[kk][2] = *reinterpret_cast<const uint32_t*>(s + (row0 + g) * LDS + kk * 16 + 8 + 2 * t);
-    a[kk][3] = *reinterpret_cast<const uint32_t*>(s + (row0 + g + 8) * LDS + kk * 16 + 8 + 2 * t);
+  for (int kk = 0; kk < 4; ++kk)
+    ldsm_x4(a[kk], s + (row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + kk * 16 + (lane >> 4) * 8);
+}
+// acc (16 x 8 tile) = A(16 x 64) * Bsrc[rows n0 .. n0+7][0..63]^T ; Bsrc row-major (k contiguous)
+__device__ __forceinline__ void gemm_nt_16x8(float (&acc)[4], const uint32_t (&a)[4][4], const __nv_bfloat16* bsrc,
+                                             int n0, int lane) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int kk2 = 0; kk2 < 2; ++kk2) {
+    uint32_t b[4];  // (b0, b1) of k16 step 2*kk2 and of step 2*kk2+1
+    ldsm_x4(b, bsrc + (n0 + (lane & 7)) * LDS + kk2 * 32 + (lane >> 3) * 8);
+    mma16816(acc, a[2 * kk2], b[0], b[1]);
+    mma16816(acc, a[2 * kk2 + 1], b[2], b[3]);
   }
 }
-// acc[nt] (16 x 8 tile nt of 16 x 16) = A(16 x 64) * Bsrc[rows n0 .. n0+15][0..63]^T
 __device__ __forceinline__ void gemm_nt_16x16(float (&acc)[2][4], const uint32_t (&a)[4][4], const __nv_bfloat16* bsrc,
-                                              int n0, int g, int t) {
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(bsrc + (n0 + nt * 8 + g) * LDS + kk * 16 + 2 * t);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(bsrc + (n0 + nt * 8 + g) * LDS + kk * 16 + 8 + 2 * t);
-      mma16816(acc[nt], a[kk], b0, b1);
-    }
-  }
+                                              int n0, int lane) {
+  gemm_nt_16x8(acc[0], a, bsrc, n0, lane);
+  gemm_nt_16x8(acc[1], a, bsrc, n0 + 8, lane);
 }
 // acc[dt] (16 x 64 output, 8 d-tiles) += P(16 x 16, as A fragment) * Bsrc[rows k0 .. k0+15][0..63]
+// Bsrc is [k][n] (n contiguous): transposing ldmatrix.x4 yields (b0, b1) of two d-tiles at once.
 __device__ __forceinline__ void gemm_pv_16x64(float (&acc)[8][4], const uint32_t (&pa)[4], const __nv_bfloat16* bsrc,
                                               int k0, int lane) {
 #pragma unroll
-  for (int dt = 0; dt < 8; ++dt) {
-    uint32_t b0, b1;
-    ldsm_x2_trans(b0, b1, bsrc + (k0 + (lane & 15)) * LDS + dt * 8);
-    mma16816(acc[dt], pa, b0, b1);
+  for (int dp = 0; dp < 4; ++dp) {
+    uint32_t b[4];
+    ldsm_x4_trans(b, bsrc + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (dp * 2 + (lane >> 4)) * 8);
+    mma16816(acc[2 * dp], pa, b[0], b[1]);
+    mma16816(acc[2 * dp + 1], pa, b[2], b[3]);
   }
 }
 
 // qkv: [B, L, 3, H, 64] bf16; out: [B, L, H*64] bf16; lse: [B, H, L] fp32 (log2 domain: m + log2(sum))
-__global__ void __launch_bounds__(128)
+// One CTA per (batch, head), one warp per 16 query rows; K and V of the head are staged once
+// (zero padded to a multiple of 64 keys) and consumed in 64-key blocks with an online softmax.
+__global__ void __launch_bounds__(512)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int B,
-                int L, int H, float scale_log2, int Lp) {
+                int L, int H, float scale_log2, int Lp, int Lk) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-  __nv_bfloat16* sK = sQ + 64 * LDS;
-  __nv_bfloat16* sV = sK + Lp * LDS;
-  const int bh = blockIdx.y, b = bh / H, h = bh % H;
-  const int q0 = blockIdx.x * 64;
+  __nv_bfloat16* sK = sQ + Lp * LDS;
+  __nv_bfloat16* sV = sK + Lk * LDS;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const long long rs = 3LL * H * HD;
   const __nv_bfloat16* base = qkv + (long long)b * L * rs + h * HD;
-  stage_rows(sQ, base, rs, q0, 64, L);
-  stage_rows(sK, base + (long long)H * HD, rs, 0, Lp, L);
-  stage_rows(sV, base + 2LL * H * HD, rs, 0, Lp, L);
+  stage_rows(sQ, base, rs, 0, Lp, L);
+  stage_rows(sK, base + (long long)H * HD, rs, 0, Lk, L);
+  stage_rows(sV, base + 2LL * H * HD, rs, 0, Lk, L);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   uint32_t qa[4][4];
-  load_a_frags(qa, sQ, warp * 16, g, t);
+  load_a_frags(qa, sQ, warp * 16, lane);
   float o[8][4];
 #pragma unroll
   for (int dt = 0; dt < 8; ++dt)
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[dt][j] = 0.f;
   float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
-  for (int k0 = 0; k0 < Lp; k0 += 16) {
-    float s[2][4];
-    gemm_nt_16x16(s, qa, sK, k0, g, t);
+  for (int kb = 0; kb < Lk; kb += 64) {
+    float s[8][4];
     float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
+    for (int nt = 0; nt < 8; ++nt) {
+      gemm_nt_16x8(s[nt], qa, sK, kb + nt * 8, lane);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int key = k0 + nt * 8 + 2 * t + (j & 1);
+        const int key = kb + nt * 8 + 2 * t + (j & 1);
         s[nt][j] = key < L ? s[nt][j] * scale_log2 : -CUDART_INF_F;
       }
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
@@ -344,12 +359,12 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: key kb is always < L
     const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);
     m0 = mn0; m1 = mn1;
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
+    for (int nt = 0; nt < 8; ++nt) {
       s[nt][0] = exp2f(s[nt][0] - m0); s[nt][1] = exp2f(s[nt][1] - m0);
       s[nt][2] = exp2f(s[nt][2] - m1); s[nt][3] = exp2f(s[nt][3] - m1);
       rs0 += s[nt][0] + s[nt][1];
@@ -361,12 +376,16 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     for (int dt = 0; dt < 8; ++dt) {
       o[dt][0] *= al0; o[dt][1] *= al0; o[dt][2] *= al1; o[dt][3] *= al1;
     }
-    const uint32_t pa[4] = {pack2(s[0][0], s[0][1]), pack2(s[0][2], s[0][3]), pack2(s[1][0], s[1][1]), pack2(s[1][2], s[1][3])};
-    gemm_pv_16x64(o, pa, sV, k0, lane);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t pa[4] = {pack2(s[2 * ks][0], s[2 * ks][1]), pack2(s[2 * ks][2], s[2 * ks][3]),
+                              pack2(s[2 * ks + 1][0], s[2 * ks + 1][1]), pack2(s[2 * ks + 1][2], s[2 * ks + 1][3])};
+      gemm_pv_16x64(o, pa, sV, kb + ks * 16, lane);
+    }
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
   const float inv0 = 1.f / l0, inv1 = 1.f / l1;
   __nv_bfloat16* ob = out + (long long)b * L * H * HD + h * HD;
 #pragma unroll
@@ -431,8 +450,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   // ---------------- phase 1: dQ[tile] = sum_keys dS K,   dS = P * (dP - D) * scale
   {
     uint32_t qa[4][4], da[4][4];
-    load_a_frags(qa, sQ, tile0, g, t);
-    load_a_frags(da, sdO, tile0, g, t);
+    load_a_frags(qa, sQ, tile0, lane);
+    load_a_frags(da, sdO, tile0, lane);
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt)
 #pragma unroll
@@ -441,8 +460,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     const float ls0 = sLse[r0], ls1 = sLse[r1], d0 = sD[r0], d1 = sD[r1];
     for (int k0 = 0; k0 < Lp; k0 += 16) {
       float s[2][4], dp[2][4];
-      gemm_nt_16x16(s, qa, sK, k0, g, t);
-      gemm_nt_16x16(dp, da, sV, k0, g, t);
+      gemm_nt_16x16(s, qa, sK, k0, lane);
+      gemm_nt_16x16(dp, da, sV, k0, lane);
       uint32_t pa[4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
@@ -467,8 +486,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   // ---------------- phase 2: dV[tile] = sum_q P^T dO;  dK[tile] = sum_q dS^T Q
   {
     uint32_t ka[4][4], va[4][4];
-    load_a_frags(ka, sK, tile0, g, t);
-    load_a_frags(va, sV, tile0, g, t);
+    load_a_frags(ka, sK, tile0, lane);
+    load_a_frags(va, sV, tile0, lane);
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt)
 #pragma unroll
@@ -476,8 +495,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     const int key0 = tile0 + g, key1 = key0 + 8;
     for (int q0 = 0; q0 < Lp; q0 += 16) {
       float st[2][4], dpt[2][4];
-      gemm_nt_16x16(st, ka, sQ, q0, g, t);     // S^T[key][query]
-      gemm_nt_16x16(dpt, va, sdO, q0, g, t);   // dP^T[key][query]
+      gemm_nt_16x16(st, ka, sQ, q0, lane);     // S^T[key][query]
+      gemm_nt_16x16(dpt, va, sdO, q0, lane);   // dP^T[key][query]
       uint32_t pta[4], dsa[4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
@@ -605,16 +624,16 @@ int saicv_token_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int b, 
 
 int saicv_attention_fwd(const void* qkv, void* out, float* lse, int b, int l, int h, int d, float scale, void* stream) {
   if (d != HD || l > 256 || l < 1) return set_error("saicv_attention_fwd: supports head_dim 64 and 1 <= L <= 256 (d=%d L=%d)", d, l);
-  const int Lp = (l + 15) / 16 * 16;
-  const size_t smem = (size_t)(64 + 2 * Lp) * LDS * 2;
+  const int Lp = (l + 15) / 16 * 16, Lk = (l + 63) / 64 * 64;
+  const size_t smem = (size_t)(Lp + 2 * Lk) * LDS * 2;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 + 2 * 256) * LDS * 2);
+    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 + 2 * 256) * LDS * 2);
     attr = true;
   }
-  dim3 grid((l + 63) / 64, b * h);
-  attn_fwd_kernel<<<grid, 128, smem, ST>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out),
-                                          lse, b, l, h, scale * 1.4426950408889634f, Lp);
+  attn_fwd_kernel<<<b * h, (Lp / 16) * 32, smem, ST>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                      reinterpret_cast<__nv_bfloat16*>(out), lse, b, l, h,
+                                                      scale * 1.4426950408889634f, Lp, Lk);
   return check_launch("attn_fwd_kernel");
 }
 

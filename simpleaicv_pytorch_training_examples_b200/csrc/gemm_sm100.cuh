@@ -2,11 +2,11 @@
 //
 //   D[M, N] (+ split-K partials) = A[M, K] * B[N, K]^T     bf16 x bf16 -> fp32 (TMEM)
 //
-// One CTA per SM, 256 threads:
+// One CTA per SM, 384 threads:
 //   warp 0      TMA producer (one lane)        global -> 128B-swizzled smem ring
 //   warp 1      MMA issuer   (one lane)        tcgen05.mma, accumulators double-buffered in TMEM
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue: tcgen05.ld -> registers -> (bias/act) -> smem -> TMA store
+//   warps 4..11 epilogue: tcgen05.ld -> registers -> (bias/act/residual) -> smem -> TMA store
 //
 // Operand feeding modes (runtime, so that fprop / dgrad / wgrad of linear layers and of NHWC
 // convolutions all go through this one kernel):
@@ -27,7 +27,7 @@ enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_GELU = 4, EPI_DIRECT = 8, EPI_RESID
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
 constexpr int kStoreBufBytes = 16384;  // 128 rows x 128 B
 constexpr int kSmemBudget = 232448 - 1024 /*align slack*/ - 512 /*barriers*/;
 
@@ -110,7 +110,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     fence_barrier_init();
   }
@@ -248,13 +248,24 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncwarp();
   } else if (warp >= 4) {
     // ================================================================ epilogue
-    const int q = warp & 3;  // TMEM sub-partition of this warp
-    const int epi_tid = threadIdx.x - 128;
+    // 8 warps: warp e handles TMEM sub-partition (lanes) e%4 and column half e/4 of every tile, so
+    // two warps drain each 32-lane quadrant concurrently.  Each half owns one 16 KB staging buffer
+    // and its own TMA-store bulk groups.
+    const int e = warp - 4;
+    const int q = e & 3;
+    const int half = e >> 2;
+    const int gtid = threadIdx.x - 128 - half * 128;  // 0..127 inside the half
     const int row_in_tile = q * 32 + lane;
+    const uint32_t bar_id = 1 + half;
+    uint8_t* const sbuf = sD + half * kStoreBufBytes;
     int as = 0;
     uint32_t aphase = 0;
-    int sbuf = 0;
     const bool direct = (p.epi_flags & EPI_DIRECT) != 0;
+    // chunk (32 columns) range of this half: whole 64-column bf16 slices, or 32-column fp32 slices
+    constexpr int NCH = BN / 32;
+    const int split_at = p.out_f32 ? (NCH + 1) / 2 : 2 * ((BN / 64 + 1) / 2);
+    const int c_begin = half ? split_at : 0;
+    const int c_end = half ? NCH : split_at;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int n_blk = w % num_n;
       const int t = w / num_n;
@@ -265,25 +276,47 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       const long long row = m0 + row_in_tile;
+      if (c_begin >= c_end) {  // nothing to drain for this half (narrow tiles): release at once
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
+        const int col0 = n0 + c * 32;
+        // operands of the epilogue are requested before the TMEM load so their latency overlaps it
+        float bv = 0.f;
+        if ((p.epi_flags & EPI_BIAS) && col0 + lane < p.N) bv = __ldg(p.bias + col0 + lane);
+        float4 rf[8];
+        uint4 rb[4];
+        const bool has_rf = (p.epi_flags & EPI_RESID) && row < p.M;
+        const bool has_rb = (p.epi_flags & EPI_RESID_BF16) && row < p.M;
+        if (has_rf) {
+          const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ldd + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rf[j] = (col0 + 4 * j < p.N) ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (has_rb) {
+          const uint4* rp = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const __nv_bfloat16*>(p.resid_bf16) + row * p.ldd + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rb[j] = (col0 + 8 * j < p.N) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+        }
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
-        if (c == BN / 32 - 1) {
-          // all accumulator columns of this buffer are in registers: hand TMEM back
+        if (c == c_end - 1) {
+          // all accumulator columns this warp owns are in registers: hand TMEM back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
-        const int col0 = n0 + c * 32;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         if (p.epi_flags & EPI_BIAS) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+          for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, bv, j);
         }
         if (p.epi_flags & EPI_GELU) {
 #pragma unroll
@@ -293,30 +326,21 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        if ((p.epi_flags & EPI_RESID) && row < p.M) {
-          const float* rp = p.resid + row * p.ldd + col0;
+        if (has_rf) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < p.N) {
-              const float4 rv = *reinterpret_cast<const float4*>(rp + j);
-              f[j] += rv.x; f[j + 1] += rv.y; f[j + 2] += rv.z; f[j + 3] += rv.w;
-            }
+          for (int j = 0; j < 8; ++j) {
+            f[4 * j] += rf[j].x; f[4 * j + 1] += rf[j].y; f[4 * j + 2] += rf[j].z; f[4 * j + 3] += rf[j].w;
           }
         }
-        if ((p.epi_flags & EPI_RESID_BF16) && row < p.M) {
-          const uint4* rp = reinterpret_cast<const uint4*>(
-              reinterpret_cast<const __nv_bfloat16*>(p.resid_bf16) + row * p.ldd + col0);
+        if (has_rb) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (col0 + 8 * j < p.N) {
-              const uint4 rv = __ldg(rp + j);
-              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+            const uint32_t wv[4] = {rb[j].x, rb[j].y, rb[j].z, rb[j].w};
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 ab = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
-                f[8 * j + 2 * t] += ab.x;
-                f[8 * j + 2 * t + 1] += ab.y;
-              }
+            for (int u = 0; u < 4; ++u) {
+              const float2 ab = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[u]));
+              f[8 * j + 2 * u] += ab.x;
+              f[8 * j + 2 * u + 1] += ab.y;
             }
           }
         }
@@ -341,60 +365,58 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         } else if (p.out_f32) {
           // one 128 B (32 x fp32) slice per TMA store
-          if (epi_tid == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
-          uint8_t* buf = sD + sbuf * kStoreBufBytes + row_in_tile * 128;
+          if (gtid == 0) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, 128);
+          uint8_t* buf = sbuf + row_in_tile * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(buf + ((j ^ (row_in_tile & 7)) << 4)) =
                 make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (epi_tid == 0) {
+          named_bar_sync(bar_id, 128);
+          if (gtid == 0) {
             if (col0 < p.N) {
               asm volatile(
                   "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                       reinterpret_cast<uint64_t>(&tmD)),
-                  "r"(smem_u32(sD + sbuf * kStoreBufBytes)), "r"(col0), "r"(m0), "r"(split)
+                  "r"(smem_u32(sbuf)), "r"(col0), "r"(m0), "r"(split)
                   : "memory");
             }
             tma_store_commit();
           }
-          sbuf ^= 1;
         } else {
           // bf16: two 32-column chunks make one 128 B (64 x bf16) slice
-          const int half = c & 1;
-          if (half == 0) {
-            if (epi_tid == 0) tma_store_wait_read<1>();
-            named_bar_sync(1, 128);
+          const int part = (c - c_begin) & 1;
+          if (part == 0) {
+            if (gtid == 0) tma_store_wait_read<0>();
+            named_bar_sync(bar_id, 128);
           }
-          uint8_t* buf = sD + sbuf * kStoreBufBytes + row_in_tile * 128;
+          uint8_t* buf = sbuf + row_in_tile * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(buf + (((half * 4 + j) ^ (row_in_tile & 7)) << 4)) =
+            *reinterpret_cast<uint4*>(buf + (((part * 4 + j) ^ (row_in_tile & 7)) << 4)) =
                 make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                            pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-          if (half == 1 || c == BN / 32 - 1) {
+          if (part == 1) {
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (epi_tid == 0) {
+            named_bar_sync(bar_id, 128);
+            if (gtid == 0) {
               const int scol = n0 + (c >> 1) * 64;
               if (scol < p.N) {
                 asm volatile(
                     "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                         reinterpret_cast<uint64_t>(&tmD)),
-                    "r"(smem_u32(sD + sbuf * kStoreBufBytes)), "r"(scol), "r"(m0), "r"(split)
+                    "r"(smem_u32(sbuf)), "r"(scol), "r"(m0), "r"(split)
                     : "memory");
               }
               tma_store_commit();
             }
-            sbuf ^= 1;
           }
         }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (epi_tid == 0) tma_store_wait<0>();
+    if (gtid == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();

@@ -46,9 +46,9 @@ def train_classification(train_loader, model, criterion, optimizer, scheduler, e
     group = getattr(config, 'group', None)
     world = _world()
     iter_index = 1
-    for _, data in enumerate(train_loader):
-        images = data['image'].cuda(non_blocking=True)
-        labels = data['label'].cuda(non_blocking=True)
+    from .utils import CudaPrefetcher
+    for _, data in enumerate(CudaPrefetcher(train_loader)):
+        images, labels = data['image'], data['label']
         bad = (~torch.isfinite(images)).any()
         if labels.dtype.is_floating_point:
             bad = bad | (~torch.isfinite(labels)).any()

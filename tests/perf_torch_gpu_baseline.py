@@ -14,7 +14,47 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import convnets  # noqa: E402
+from oracle import convnets, vit  # noqa: E402
+
+
+def run_vit(a):
+    """ViT-B/16 (global_pool, soft labels, AdamW) on stock torch kernels under autocast(bf16): the
+    reference's unfused attention / MLP ops (vit.py:62-97) through oracle/vit.py's identical op sequence."""
+    dev = torch.device('cuda')
+    sd = {k: v.to(dev) for k, v in vit.init_state(a.model, 1000, 0).items()}
+    for v in sd.values():
+        v.requires_grad_(True)
+    opt = torch.optim.AdamW([{'params': [v for v in sd.values() if v.ndim > 1], 'weight_decay': 0.05},
+                             {'params': [v for v in sd.values() if v.ndim <= 1], 'weight_decay': 0.}], lr=5e-4)
+    x = torch.randn(a.batch, 3, 224, 224, device=dev)
+    lab = torch.randint(0, 1000, (a.batch,), device=dev)
+    y = torch.nn.functional.one_hot(lab, 1000).float() * 0.9 + 1e-4
+
+    def step():
+        if torch.any(torch.isinf(x)) or torch.any(torch.isnan(x)):
+            return
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            out = vit.forward(sd, x, a.model, global_pool=True)
+            loss = torch.sum(-y * torch.nn.functional.log_softmax(out.float(), dim=-1), dim=-1).mean()
+        if loss == 0. or torch.any(torch.isinf(loss)) or torch.any(torch.isnan(loss)):
+            return
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return loss.item()
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(a.steps):
+        step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / a.steps
+    print(json.dumps({'what': 'stock torch (reference GPU path) ViT-B/16 bf16 autocast, drop_path 0', 'batch': a.batch,
+                      'ms_per_step': ms, 'images_per_sec': a.batch / ms * 1e3, 'torch': torch.__version__}))
 
 
 def main():
@@ -24,7 +64,10 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--benchmark', action='store_true', help='cudnn.benchmark=True (the reference ships False + deterministic)')
     ap.add_argument('--channels-last', action='store_true')
+    ap.add_argument('--model', default='resnet50', choices=['resnet50', 'vit_base_patch16'])
     a = ap.parse_args()
+    if a.model != 'resnet50':
+        return run_vit(a)
     torch.backends.cudnn.benchmark = a.benchmark
     torch.backends.cudnn.deterministic = not a.benchmark  # tools/utils.py:106-107
     dev = torch.device('cuda')

@@ -10,3 +10,4 @@ run "smoke" python __graft_entry__.py smoke
 run "bn microbench" python tests/perf_bn_kernels.py
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --dump-ops gpurun_out/ops_r50.csv > gpurun_out/bench_r50.log 2>&1; tail -1 gpurun_out/bench_r50.log
 python bench.py --model vit_base_patch16 --steps 5 --warmup 3 --no-cpu-baseline --dump-ops gpurun_out/ops_vit.csv > gpurun_out/bench_vit.log 2>&1; tail -2 gpurun_out/bench_vit.log
+python tests/perf_torch_gpu_baseline.py --model vit_base_patch16 --steps 5 2>&1 | tail -1
