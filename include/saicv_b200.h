@@ -33,12 +33,16 @@ int saicv_sm_count(void);
 long long saicv_launch_count(void);
 
 /* ---- dense layers: nn.Linear (vit.py:57-58,87-89; resnet.py:204) ------------------------ */
-/* y[M,N] = x[M,K] w[N,K]^T (+bias) (+act) (+resid); x,w bf16; y bf16 or fp32 (out_f32). */
-int saicv_linear_fwd(const void* x, const void* w, const float* bias, const float* resid, void* y,
-                     int M, int N, int K, int flags, int out_f32, void* stream);
-/* dx[M,K] = dy[M,N] w[N,K]; dy,w bf16; dx bf16 or fp32 (+resid fp32 [M,K] when flagged). */
-int saicv_linear_dgrad(const void* dy, const void* w, const float* resid, void* dx, int M, int N,
-                       int K, int flags, int out_f32, void* stream);
+/* y[M,N] = resid + row_scale[row / rows_per_scale] * act(x[M,K] w[N,K]^T + bias); x,w bf16; y bf16
+ * or fp32 (out_f32); bias [N] fp32, resid [M,N] fp32 and row_scale (drop-path, vit.py:118-135) may
+ * be NULL. */
+int saicv_linear_fwd(const void* x, const void* w, const float* bias, const float* resid,
+                     const float* row_scale, int rows_per_scale, void* y, int M, int N, int K,
+                     int flags, int out_f32, void* stream);
+/* dx[M,K] = (dy[M,N] w[N,K]) (* gelu'(gelu_pre[M,K])) (+ resid[M,K]); dy,w,gelu_pre bf16; dx bf16
+ * or fp32; gelu_pre (the pre-activation saved by the forward, vit.py:87-89) and resid may be NULL. */
+int saicv_linear_dgrad(const void* dy, const void* w, const float* resid, const void* gelu_pre,
+                       void* dx, int M, int N, int K, int flags, int out_f32, void* stream);
 /* dw_partial[splits][N][K] (fp32) = dy[M,N]^T x[M,K], reduction over M split `splits` ways.
  * Pass splits = saicv_wgrad_splits(...) and reduce with saicv_reduce_partials. */
 int saicv_linear_wgrad(const void* dy, const void* x, float* dw_partial, int M, int N, int K,
@@ -146,11 +150,13 @@ int saicv_colsum(const void* x, float* partials, float* out, long long rows, int
 int saicv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y,
                         float* stats, long long rows, int c, float eps, void* stream);
 /* dx (fp32) = dres + LN'(dy) with dres the residual-stream gradient (may be NULL); optional bf16
- * copy of dx for the next GEMM; dgamma/dbeta (+)= column reductions (zeroed first unless
- * accumulate). */
+ * copy of dx for the next GEMM, optionally pre-multiplied per row by
+ * bf16_row_scale[row / rows_per_scale] (the drop-path scale of the branch that consumes it);
+ * dgamma/dbeta (+)= column reductions (zeroed first unless accumulate). */
 int saicv_layernorm_bwd(const void* dy, const float* x, const float* gamma, const float* stats,
-                        const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
-                        long long rows, int c, int accumulate, void* stream);
+                        const float* dres, float* dx, void* dx_bf16, const float* bf16_row_scale,
+                        int rows_per_scale, float* dgamma, float* dbeta, long long rows, int c,
+                        int accumulate, void* stream);
 /* nn.GELU() exact erf (vit.py:87-89): h = gelu(u); du = dh * gelu'(u); bf16, n % 8 == 0. */
 int saicv_gelu_fwd(const void* u, void* h, long long n, void* stream);
 int saicv_gelu_bwd(const void* dh, const void* u, void* du, long long n, void* stream);
@@ -163,8 +169,8 @@ int saicv_vit_assemble_tokens_bwd(const float* dx, float* dpos, float* dcls, voi
 /* pooled[b] = mean of tokens 1..l-1 (mean_pool, vit.py:252-255) or token 0 (vit.py:257-258). */
 int saicv_token_pool_fwd(const float* x, float* pooled, int b, int l, int c, int mean_pool,
                          void* stream);
-int saicv_token_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int b, int l, int c,
-                         int mean_pool, void* stream);
+int saicv_token_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, const float* bf16_row_scale,
+                         int b, int l, int c, int mean_pool, void* stream);
 /* MultiHeadAttention core (vit.py:66-76): qkv bf16 [b][l][3][h][d] -> out bf16 [b][l][h*d] =
  * softmax(q k^T * scale) v, fused (the l x l matrix is never written); lse[b][h][l] (log2 domain)
  * is kept for the backward.  d == 64, l <= 256. */

@@ -188,8 +188,9 @@ int saicv_wgrad_splits(int out_rows, int out_cols, long long reduce_len) {
   return (int)s;
 }
 
-int saicv_linear_fwd(const void* x, const void* w, const float* bias, const float* resid, void* y,
-                     int M, int N, int K, int flags, int out_f32, void* stream) {
+int saicv_linear_fwd(const void* x, const void* w, const float* bias, const float* resid,
+                     const float* row_scale, int rows_per_scale, void* y, int M, int N, int K, int flags,
+                     int out_f32, void* stream) {
   if (!ensure_init()) return 1;
   if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (K % 8) || (N % (out_f32 ? 4 : 8)))
     return set_error("saicv_linear_fwd: unaligned operand (M=%d N=%d K=%d)", M, N, K);
@@ -202,14 +203,16 @@ int saicv_linear_fwd(const void* x, const void* w, const float* bias, const floa
   p.M = M; p.N = N; p.num_kb = (K + BK - 1) / BK; p.kb_per_split = p.num_kb; p.splits = 1;
   p.a_mode = A_K2D; p.b_mode = B_K2D;
   p.g.P = p.g.Q = 1; p.g.cchunks = 1; p.g.S = 1; p.g.R = 1;
-  p.epi_flags = flags | (bias ? EPI_BIAS : 0) | (resid ? EPI_RESID : 0);
-  if (!bias) p.epi_flags &= ~EPI_BIAS;
+  p.epi_flags = (flags & (EPI_RELU | EPI_GELU | EPI_DIRECT)) | (bias ? EPI_BIAS : 0) | (resid ? EPI_RESID : 0) |
+                (row_scale ? EPI_ROW_SCALE : 0);
+  if (row_scale && rows_per_scale <= 0) return set_error("saicv_linear_fwd: rows_per_scale must be > 0");
+  p.row_scale = row_scale; p.rows_per_scale = rows_per_scale;
   p.out_f32 = out_f32; p.bias = bias; p.resid = resid; p.out = y; p.ldd = N; p.split_stride = 0;
   return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream);
 }
 
-int saicv_linear_dgrad(const void* dy, const void* w, const float* resid, void* dx, int M, int N,
-                       int K, int flags, int out_f32, void* stream) {
+int saicv_linear_dgrad(const void* dy, const void* w, const float* resid, const void* gelu_pre, void* dx,
+                       int M, int N, int K, int flags, int out_f32, void* stream) {
   if (!ensure_init()) return 1;
   if (!aligned16(dy) || !aligned16(w) || !aligned16(dx) || (K % 8) || (N % 8))
     return set_error("saicv_linear_dgrad: unaligned operand (M=%d N=%d K=%d)", M, N, K);
@@ -223,8 +226,9 @@ int saicv_linear_dgrad(const void* dy, const void* w, const float* resid, void* 
   p.M = M; p.N = K; p.num_kb = (N + BK - 1) / BK; p.kb_per_split = p.num_kb; p.splits = 1;
   p.a_mode = A_K2D; p.b_mode = B_MN2D;
   p.g.P = p.g.Q = 1; p.g.cchunks = 1; p.g.S = 1; p.g.R = 1;
-  p.epi_flags = (flags & ~EPI_BIAS) | (resid ? EPI_RESID : 0);
-  p.out_f32 = out_f32; p.resid = resid; p.out = dx; p.ldd = K;
+  p.epi_flags = (flags & EPI_DIRECT) | (resid ? EPI_RESID : 0) | (gelu_pre ? EPI_MUL_DGELU : 0);
+  if (gelu_pre && !aligned16(gelu_pre)) return set_error("saicv_linear_dgrad: unaligned gelu_pre");
+  p.out_f32 = out_f32; p.resid = resid; p.resid_bf16 = gelu_pre; p.out = dx; p.ldd = K;
   return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream);
 }
 

@@ -79,8 +79,8 @@ template <int NCH>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ stats, const float* __restrict__ dres, float* __restrict__ dx,
-              __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              long long M) {
+              __nv_bfloat16* __restrict__ dx_bf16, const float* __restrict__ row_scale, int rows_per_scale,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, long long M) {
   constexpr int C = NCH * 128;
   __shared__ float red[8][C];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -94,6 +94,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
   }
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < M; row += warps) {
     const float mean = stats[row], rstd = stats[M + row];
+    const float bsc = row_scale ? row_scale[row / rows_per_scale] : 1.f;
     float4 xh[NCH], d[NCH];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -119,7 +120,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
       }
       *reinterpret_cast<float4*>(dx + row * C + i * 128 + lane * 4) = o;
       if (dx_bf16)
-        *reinterpret_cast<uint2*>(dx_bf16 + row * C + i * 128 + lane * 4) = make_uint2(pack2(o.x, o.y), pack2(o.z, o.w));
+        *reinterpret_cast<uint2*>(dx_bf16 + row * C + i * 128 + lane * 4) =
+            make_uint2(pack2(o.x * bsc, o.y * bsc), pack2(o.z * bsc, o.w * bsc));
     }
   }
   // fold the 8 warps' partial dgamma / dbeta
@@ -220,7 +222,7 @@ __global__ void token_pool_fwd_kernel(const float* __restrict__ x, float* __rest
   }
 }
 __global__ void token_pool_bwd_kernel(const float* __restrict__ dpooled, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
-                                      int B, int L, int C, int mean_pool) {
+                                      const float* __restrict__ row_scale, int B, int L, int C, int mean_pool) {
   const long long total = (long long)B * L * C;
   const float inv = 1.f / (float)(L - 1);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -232,7 +234,7 @@ __global__ void token_pool_bwd_kernel(const float* __restrict__ dpooled, float* 
     if (mean_pool) v = l == 0 ? 0.f : dpooled[b * C + c] * inv;
     else v = l == 0 ? dpooled[b * C + c] : 0.f;
     dx[i] = v;
-    if (dx_bf16) dx_bf16[i] = __float2bfloat16_rn(v);
+    if (dx_bf16) dx_bf16[i] = __float2bfloat16_rn(row_scale ? v * row_scale[b] : v);
   }
 }
 
@@ -399,72 +401,105 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   }
 }
 
-// One CTA per (batch, head); Lp/16 warps.  Phase 1: each warp owns 16 query rows -> dQ.  Phase 2: each
-// warp owns 16 key rows -> dK, dV.  dqkv has the layout of qkv.
+// A fragments (16 rows x 64 k) straight from global memory (rows >= L read as zero).
+__device__ __forceinline__ void load_a_frags_global(uint32_t (&a)[4][4], const __nv_bfloat16* base, long long row_stride,
+                                                    int row0, int L, int g, int t) {
+  const int r0 = row0 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    a[kk][0] = r0 < L ? *reinterpret_cast<const uint32_t*>(base + (long long)r0 * row_stride + kk * 16 + 2 * t) : 0u;
+    a[kk][1] = r1 < L ? *reinterpret_cast<const uint32_t*>(base + (long long)r1 * row_stride + kk * 16 + 2 * t) : 0u;
+    a[kk][2] = r0 < L ? *reinterpret_cast<const uint32_t*>(base + (long long)r0 * row_stride + kk * 16 + 8 + 2 * t) : 0u;
+    a[kk][3] = r1 < L ? *reinterpret_cast<const uint32_t*>(base + (long long)r1 * row_stride + kk * 16 + 8 + 2 * t) : 0u;
+  }
+}
+// sum_d a[row][d] * b[row][d] over the 64 head dims, computed by the 4 lanes of a quad
+__device__ __forceinline__ float row_dot64(const __nv_bfloat16* a, const __nv_bfloat16* b, int t) {
+  float acc = 0.f;
+  const uint4* pa = reinterpret_cast<const uint4*>(a + t * 16);
+  const uint4* pb = reinterpret_cast<const uint4*>(b + t * 16);
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const uint4 x = pa[v], y = pb[v];
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fx = unpack2(xw[k]), fy = unpack2(yw[k]);
+      acc += fx.x * fy.x + fx.y * fy.y;
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  return acc;
+}
+
+// Backward of the fused attention.  grid = (batch*heads, 2), Lp/16 warps per CTA, ~61 KB of shared
+// memory so three CTAs share an SM:
+//   blockIdx.y == 0: each warp owns 16 query rows -> dQ      (K, V staged in smem; Q, dO tiles from global)
+//   blockIdx.y == 1: each warp owns 16 key rows   -> dK, dV  (Q, dO staged in smem; K, V tiles from global)
+// P is recomputed from the saved log-sum-exp; dS = P * (dP - D) * scale with D = rowsum(dO * O).
+// dqkv has the layout of qkv.
 __global__ void __launch_bounds__(512)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                 const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
-                int B, int L, int H, float scale, float scale_log2, int Lp) {
+                int B, int L, int H, float scale, float scale_log2, int Lp, int Lq) {
+  // Lp = L rounded up to 16 (one warp per 16 rows); Lq = L rounded up to 32 (rows staged, zero padded)
   extern __shared__ __align__(16) uint8_t smem_attn[];
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-  __nv_bfloat16* sK = sQ + Lp * LDS;
-  __nv_bfloat16* sV = sK + Lp * LDS;
-  __nv_bfloat16* sdO = sV + Lp * LDS;
-  float* sLse = reinterpret_cast<float*>(sdO + Lp * LDS);
+  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(smem_attn);  // K (phase 0) or Q (phase 1)
+  __nv_bfloat16* sY = sX + Lq * LDS;                                // V (phase 0) or dO (phase 1)
+  float* sLse = reinterpret_cast<float*>(sY + Lq * LDS);
   float* sD = sLse + Lp;
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
-  const long long rs = 3LL * H * HD;
-  const __nv_bfloat16* base = qkv + (long long)b * L * rs + h * HD;
-  const __nv_bfloat16* ob = out + (long long)b * L * H * HD + h * HD;
-  const __nv_bfloat16* dob = dout + (long long)b * L * H * HD + h * HD;
-  stage_rows(sQ, base, rs, 0, Lp, L);
-  stage_rows(sK, base + (long long)H * HD, rs, 0, Lp, L);
-  stage_rows(sV, base + 2LL * H * HD, rs, 0, Lp, L);
-  stage_rows(sdO, dob, (long long)H * HD, 0, Lp, L);
-  // D[i] = sum_d dO[i][d] * O[i][d]; lse
-  for (int r = threadIdx.x; r < Lp; r += blockDim.x) {
-    float acc = 0.f;
-    if (r < L) {
-      const uint4* po = reinterpret_cast<const uint4*>(ob + (long long)r * H * HD);
-      const uint4* pd = reinterpret_cast<const uint4*>(dob + (long long)r * H * HD);
-#pragma unroll
-      for (int v = 0; v < HD / 8; ++v) {
-        const uint4 a = po[v], d = pd[v];
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 fa = unpack2(aw[k]), fd = unpack2(dw[k]);
-          acc += fa.x * fd.x + fa.y * fd.y;
-        }
-      }
+  const int phase = blockIdx.y;
+  const long long rs = 3LL * H * HD, os = (long long)H * HD;
+  const __nv_bfloat16* qb = qkv + (long long)b * L * rs + h * HD;
+  const __nv_bfloat16* kb_ = qb + (long long)H * HD;
+  const __nv_bfloat16* vb = qb + 2LL * H * HD;
+  const __nv_bfloat16* ob = out + (long long)b * L * os + h * HD;
+  const __nv_bfloat16* dob = dout + (long long)b * L * os + h * HD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int tile0 = warp * 16;
+  __nv_bfloat16* dbase = dqkv + (long long)b * L * rs + h * HD;
+  if (phase == 0) {
+    stage_rows(sX, kb_, rs, 0, Lq, L);
+    stage_rows(sY, vb, rs, 0, Lq, L);
+  } else {
+    stage_rows(sX, qb, rs, 0, Lq, L);
+    stage_rows(sY, dob, os, 0, Lq, L);
+    for (int r = threadIdx.x; r < Lp; r += blockDim.x) sLse[r] = r < L ? lse[(long long)bh * L + r] : 0.f;
+    // D[i] for every query: 4 lanes per row
+    for (int r = (threadIdx.x >> 2); r < Lp; r += (blockDim.x >> 2)) {
+      const float dsum = r < L ? row_dot64(ob + (long long)r * os, dob + (long long)r * os, t) : 0.f;
+      if (t == 0) sD[r] = dsum;
     }
-    sD[r] = acc;
-    sLse[r] = r < L ? lse[(long long)bh * L + r] : 0.f;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int tile0 = warp * 16;  // this warp's 16 rows (queries in phase 1, keys in phase 2)
-  __nv_bfloat16* dbase = dqkv + (long long)b * L * rs + h * HD;
   float acc1[8][4], acc2[8][4];
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc1[dt][j] = acc2[dt][j] = 0.f;
 
-  // ---------------- phase 1: dQ[tile] = sum_keys dS K,   dS = P * (dP - D) * scale
-  {
+  if (phase == 0) {
+    // ---------------- dQ[tile] = sum_keys dS K
     uint32_t qa[4][4], da[4][4];
-    load_a_frags(qa, sQ, tile0, lane);
-    load_a_frags(da, sdO, tile0, lane);
-#pragma unroll
-    for (int dt = 0; dt < 8; ++dt)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc1[dt][j] = 0.f;
+    load_a_frags_global(qa, qb, rs, tile0, L, g, t);
+    load_a_frags_global(da, dob, os, tile0, L, g, t);
     const int r0 = tile0 + g, r1 = r0 + 8;
-    const float ls0 = sLse[r0], ls1 = sLse[r1], d0 = sD[r0], d1 = sD[r1];
-    for (int k0 = 0; k0 < Lp; k0 += 16) {
-      float s[2][4], dp[2][4];
-      gemm_nt_16x16(s, qa, sK, k0, lane);
-      gemm_nt_16x16(dp, da, sV, k0, lane);
-      uint32_t pa[4];
+    const float ls0 = r0 < L ? lse[(long long)bh * L + r0] : 0.f, ls1 = r1 < L ? lse[(long long)bh * L + r1] : 0.f;
+    const float d0 = r0 < L ? row_dot64(ob + (long long)r0 * os, dob + (long long)r0 * os, t) : 0.f;
+    const float d1 = r1 < L ? row_dot64(ob + (long long)r1 * os, dob + (long long)r1 * os, t) : 0.f;
+    // 32 keys per step: 8 independent accumulation chains keep the tensor pipe busier
+    for (int k0 = 0; k0 < Lq; k0 += 32) {
+      float s[4][4], dp[4][4];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
+      for (int nt = 0; nt < 4; ++nt) {
+        gemm_nt_16x8(s[nt], qa, sX, k0 + nt * 8, lane);
+        gemm_nt_16x8(dp[nt], da, sY, k0 + nt * 8, lane);
+      }
+      uint32_t pa[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
         float ds[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -472,31 +507,27 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
           const float p = key < L ? exp2f(s[nt][j] * scale_log2 - (j < 2 ? ls0 : ls1)) : 0.f;
           ds[j] = p * (dp[nt][j] - (j < 2 ? d0 : d1)) * scale;
         }
-        pa[nt * 2] = pack2(ds[0], ds[1]);
-        pa[nt * 2 + 1] = pack2(ds[2], ds[3]);
+        pa[nt >> 1][(nt & 1) * 2] = pack2(ds[0], ds[1]);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack2(ds[2], ds[3]);
       }
-      gemm_pv_16x64(acc1, pa, sK, k0, lane);
+      gemm_pv_16x64(acc1, pa[0], sX, k0, lane);
+      gemm_pv_16x64(acc1, pa[1], sX, k0 + 16, lane);
     }
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) {
       if (r0 < L) *reinterpret_cast<uint32_t*>(dbase + (long long)r0 * rs + dt * 8 + 2 * t) = pack2(acc1[dt][0], acc1[dt][1]);
       if (r1 < L) *reinterpret_cast<uint32_t*>(dbase + (long long)r1 * rs + dt * 8 + 2 * t) = pack2(acc1[dt][2], acc1[dt][3]);
     }
-  }
-  // ---------------- phase 2: dV[tile] = sum_q P^T dO;  dK[tile] = sum_q dS^T Q
-  {
+  } else {
+    // ---------------- dV[tile] = sum_q P^T dO;  dK[tile] = sum_q dS^T Q
     uint32_t ka[4][4], va[4][4];
-    load_a_frags(ka, sK, tile0, lane);
-    load_a_frags(va, sV, tile0, lane);
-#pragma unroll
-    for (int dt = 0; dt < 8; ++dt)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc1[dt][j] = acc2[dt][j] = 0.f;
+    load_a_frags_global(ka, kb_, rs, tile0, L, g, t);
+    load_a_frags_global(va, vb, rs, tile0, L, g, t);
     const int key0 = tile0 + g, key1 = key0 + 8;
     for (int q0 = 0; q0 < Lp; q0 += 16) {
       float st[2][4], dpt[2][4];
-      gemm_nt_16x16(st, ka, sQ, q0, lane);     // S^T[key][query]
-      gemm_nt_16x16(dpt, va, sdO, q0, lane);   // dP^T[key][query]
+      gemm_nt_16x16(st, ka, sX, q0, lane);     // S^T[key][query]
+      gemm_nt_16x16(dpt, va, sY, q0, lane);    // dP^T[key][query]
       uint32_t pta[4], dsa[4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
@@ -513,8 +544,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
         dsa[nt * 2] = pack2(ds[0], ds[1]);
         dsa[nt * 2 + 1] = pack2(ds[2], ds[3]);
       }
-      gemm_pv_16x64(acc1, pta, sdO, q0, lane);  // dV += P^T dO
-      gemm_pv_16x64(acc2, dsa, sQ, q0, lane);   // dK += dS^T Q
+      gemm_pv_16x64(acc1, pta, sY, q0, lane);  // dV += P^T dO
+      gemm_pv_16x64(acc2, dsa, sX, q0, lane);  // dK += dS^T Q
     }
     __nv_bfloat16* dk = dbase + (long long)H * HD;
     __nv_bfloat16* dv = dbase + 2LL * H * HD;
@@ -563,8 +594,9 @@ int saicv_layernorm_fwd(const float* x, const float* gamma, const float* beta, v
 }
 
 int saicv_layernorm_bwd(const void* dy, const float* x, const float* gamma, const float* stats, const float* dres,
-                        float* dx, void* dx_bf16, float* dgamma, float* dbeta, long long rows, int c, int accumulate,
-                        void* stream) {
+                        float* dx, void* dx_bf16, const float* bf16_row_scale, int rows_per_scale, float* dgamma,
+                        float* dbeta, long long rows, int c, int accumulate, void* stream) {
+  if (bf16_row_scale && rows_per_scale <= 0) return set_error("saicv_layernorm_bwd: rows_per_scale must be > 0");
   if (!accumulate) {
     cudaMemsetAsync(dgamma, 0, sizeof(float) * c, ST);
     cudaMemsetAsync(dbeta, 0, sizeof(float) * c, ST);
@@ -573,11 +605,11 @@ int saicv_layernorm_bwd(const void* dy, const float* x, const float* gamma, cons
   const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(dy);
   __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   switch (c) {
-    case 768: ln_bwd_kernel<6><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, dgamma, dbeta, rows); break;
-    case 1024: ln_bwd_kernel<8><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, dgamma, dbeta, rows); break;
-    case 1280: ln_bwd_kernel<10><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, dgamma, dbeta, rows); break;
-    case 256: ln_bwd_kernel<2><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, dgamma, dbeta, rows); break;
-    case 128: ln_bwd_kernel<1><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, dgamma, dbeta, rows); break;
+    case 768: ln_bwd_kernel<6><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, dgamma, dbeta, rows); break;
+    case 1024: ln_bwd_kernel<8><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, dgamma, dbeta, rows); break;
+    case 1280: ln_bwd_kernel<10><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, dgamma, dbeta, rows); break;
+    case 256: ln_bwd_kernel<2><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, dgamma, dbeta, rows); break;
+    case 128: ln_bwd_kernel<1><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, dgamma, dbeta, rows); break;
     default: return set_error("saicv_layernorm_bwd: unsupported width %d", c);
   }
   return check_launch("ln_bwd_kernel");
@@ -615,10 +647,10 @@ int saicv_token_pool_fwd(const float* x, float* pooled, int b, int l, int c, int
   return check_launch("token_pool_fwd_kernel");
 }
 
-int saicv_token_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int b, int l, int c, int mean_pool,
-                         void* stream) {
+int saicv_token_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, const float* bf16_row_scale, int b, int l,
+                         int c, int mean_pool, void* stream) {
   token_pool_bwd_kernel<<<grid_1d((long long)b * l * c), 256, 0, ST>>>(dpooled, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16),
-                                                                       b, l, c, mean_pool);
+                                                                       bf16_row_scale, b, l, c, mean_pool);
   return check_launch("token_pool_bwd_kernel");
 }
 
@@ -641,16 +673,17 @@ int saicv_attention_bwd(const void* qkv, const void* out, const void* dout, cons
                         int h, int d, float scale, void* stream) {
   if (d != HD || l > 256 || l < 1) return set_error("saicv_attention_bwd: supports head_dim 64 and 1 <= L <= 256 (d=%d L=%d)", d, l);
   const int Lp = (l + 15) / 16 * 16;
-  const size_t smem = (size_t)4 * Lp * LDS * 2 + (size_t)2 * Lp * 4;
+  const int Lq = (l + 31) / 32 * 32;
+  const size_t smem = (size_t)2 * Lq * LDS * 2 + (size_t)2 * Lp * 4;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 256 * LDS * 2 + 2 * 256 * 4);
+    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * LDS * 2 + 2 * 256 * 4);
     attr = true;
   }
-  attn_bwd_kernel<<<b * h, (Lp / 16) * 32, smem, ST>>>(
+  attn_bwd_kernel<<<dim3(b * h, 2), (Lp / 16) * 32, smem, ST>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(out),
       reinterpret_cast<const __nv_bfloat16*>(dout), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), b, l, h, scale,
-      scale * 1.4426950408889634f, Lp);
+      scale * 1.4426950408889634f, Lp, Lq);
   return check_launch("attn_bwd_kernel");
 }
 

@@ -23,7 +23,8 @@ namespace saicv {
 
 enum : int { A_K2D = 0, A_IM2COL = 1, A_MN2D = 2 };
 enum : int { B_K2D = 0, B_MN2D = 2, B_IM2COL = 3 };
-enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_GELU = 4, EPI_DIRECT = 8, EPI_RESID = 16, EPI_RESID_BF16 = 32 };
+enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_GELU = 4, EPI_DIRECT = 8, EPI_RESID = 16, EPI_RESID_BF16 = 32,
+              EPI_MUL_DGELU = 64, EPI_ROW_SCALE = 128 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -64,7 +65,9 @@ struct GemmParams {
   int out_f32;         // 1: D is fp32, else bf16
   const float* bias;   // [N] or null
   const float* resid;  // fp32 [M, ldd] residual added in the epilogue (EPI_RESID) or null
-  const void* resid_bf16;  // bf16 [M, ldd] tensor added in the epilogue (EPI_RESID_BF16) or null
+  const void* resid_bf16;  // bf16 [M, ldd]: added (EPI_RESID_BF16) or, as pre-activation u, D *= gelu'(u) (EPI_MUL_DGELU)
+  const float* row_scale;  // EPI_ROW_SCALE: D = resid + row_scale[row / rows_per_scale] * (acc + bias) (drop-path)
+  int rows_per_scale;
   void* out;           // direct-store path
   long long ldd;       // leading dimension of D in elements
   long long split_stride;  // elements between split-K partial outputs
@@ -72,6 +75,9 @@ struct GemmParams {
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
 template <int BN>
@@ -290,7 +296,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float4 rf[8];
         uint4 rb[4];
         const bool has_rf = (p.epi_flags & EPI_RESID) && row < p.M;
-        const bool has_rb = (p.epi_flags & EPI_RESID_BF16) && row < p.M;
+        const bool has_rb = (p.epi_flags & (EPI_RESID_BF16 | EPI_MUL_DGELU)) && row < p.M;
+        float rscale = 1.f;
+        if ((p.epi_flags & EPI_ROW_SCALE) && row < p.M) rscale = __ldg(p.row_scale + row / p.rows_per_scale);
         if (has_rf) {
           const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ldd + col0);
 #pragma unroll
@@ -326,6 +334,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
+        if (p.epi_flags & EPI_ROW_SCALE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= rscale;
+        }
         if (has_rf) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -339,8 +351,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float2 ab = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[u]));
-              f[8 * j + 2 * u] += ab.x;
-              f[8 * j + 2 * u + 1] += ab.y;
+              if (p.epi_flags & EPI_MUL_DGELU) {
+                f[8 * j + 2 * u] *= gelu_erf_grad(ab.x);
+                f[8 * j + 2 * u + 1] *= gelu_erf_grad(ab.y);
+              } else {
+                f[8 * j + 2 * u] += ab.x;
+                f[8 * j + 2 * u + 1] += ab.y;
+              }
             }
           }
         }

@@ -38,11 +38,13 @@ class _Linear:
             self.version = ver
         self.b_pad[:w.shape[0]].copy_(self.mod.bias.detach())
 
-    def fwd(self, x, resid=None, out_f32=False):
-        return ops.linear_fwd(x, self.w_bf16, bias=self.b_pad, resid=resid, out_f32=out_f32)
+    def fwd(self, x, resid=None, out_f32=False, row_scale=None, rows_per_scale=0):
+        return ops.linear_fwd(x, self.w_bf16, bias=self.b_pad, resid=resid, out_f32=out_f32,
+                              row_scale=row_scale, rows_per_scale=rows_per_scale)
 
-    def bwd(self, dy, x, sink, need_dx=True):
-        """dy bf16 [M, N], x bf16 [M, K]: writes dW, db through the sink, returns dx bf16."""
+    def bwd(self, dy, x, sink, need_dx=True, gelu_pre=None):
+        """dy bf16 [M, N], x bf16 [M, K]: writes dW, db through the sink, returns dx bf16
+        (multiplied by gelu'(gelu_pre) when the input of this layer was gelu(gelu_pre))."""
         w, b = self.mod.weight, self.mod.bias
         n = w.shape[0]
         wbuf, wacc = sink.begin(w)
@@ -62,7 +64,7 @@ class _Linear:
             ops.colsum(dy, full)
             bbuf.copy_(full[:n] + (bbuf if bacc else 0))
         sink.done(b, bbuf)
-        return ops.linear_dgrad(dy, self.w_bf16) if need_dx else None
+        return ops.linear_dgrad(dy, self.w_bf16, gelu_pre=gelu_pre) if need_dx else None
 
 
 class _Block:
@@ -96,54 +98,40 @@ class _Block:
         t['qkv'] = self.qkv.fwd(t['ln1'])
         t['att'], t['lse'] = ops.attention_fwd(t['qkv'], b, l, self.heads, d, self.scale)
         s1 = t['s1'] = self._path_scale(b, l, training, x.device)
-        if s1 is None:
-            x = self.proj.fwd(t['att'], resid=x, out_f32=True)
-        else:
-            branch = self.proj.fwd(t['att'], out_f32=True)
-            x = x + (branch.view(b, l, c) * s1.view(b, 1, 1)).view(b * l, c)
+        x = self.proj.fwd(t['att'], resid=x, out_f32=True, row_scale=s1, rows_per_scale=l)
         t['x_mid'] = x
         t['ln2'], t['st2'] = ops.layernorm_fwd(x, blk.norm2.weight.detach(), blk.norm2.bias.detach(), blk.norm2.eps)
         t['u'] = self.fc1.fwd(t['ln2'])
         t['h'] = ops.gelu_fwd(t['u'])
         s2 = t['s2'] = self._path_scale(b, l, training, x.device)
-        if s2 is None:
-            x = self.fc2.fwd(t['h'], resid=x, out_f32=True)
-        else:
-            branch = self.fc2.fwd(t['h'], out_f32=True)
-            x = x + (branch.view(b, l, c) * s2.view(b, 1, 1)).view(b * l, c)
-        return x
+        return self.fc2.fwd(t['h'], resid=x, out_f32=True, row_scale=s2, rows_per_scale=l)
 
-    def _scaled(self, dxb, s, b, l):
-        if s is None:
-            return dxb
-        c = dxb.shape[1]
-        return (dxb.view(b, l, c).float() * s.view(b, 1, 1)).to(torch.bfloat16).view(b * l, c)
-
-    def _ln_bwd(self, norm, dy, x, stats, dres, sink):
+    def _ln_bwd(self, norm, dy, x, stats, dres, sink, scale, l):
+        """`scale`: drop-path scale of the branch that will consume the bf16 copy of dx."""
         gbuf, gacc = sink.begin(norm.weight)
         bbuf, bacc = sink.begin(norm.bias)
         dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-        dx = ops.layernorm_bwd(dy, x, norm.weight.detach(), stats, gbuf, bbuf, dres=dres, dx_bf16=dxb, accumulate=gacc)
+        dx = ops.layernorm_bwd(dy, x, norm.weight.detach(), stats, gbuf, bbuf, dres=dres, dx_bf16=dxb, accumulate=gacc,
+                               bf16_row_scale=scale, rows_per_scale=l)
         sink.done(norm.weight, gbuf)
         sink.done(norm.bias, bbuf)
         return dx, dxb
 
-    def backward(self, dx, dxb, t, b, l, sink):
-        """dx fp32 / dxb bf16: gradient w.r.t. the block output.  Returns (dx_in fp32, bf16 copy)."""
+    def backward(self, dx, dxb, t, b, l, sink, next_scale=None):
+        """dx fp32: gradient w.r.t. the block output; dxb: its bf16 copy already multiplied by this
+        block's MLP drop-path scale (t['s2']).  Returns (dx_in fp32, bf16 copy multiplied by
+        `next_scale`, the MLP drop-path scale of the block that consumes it)."""
         blk = self.blk
         d = dx.shape[1] // self.heads
-        # ---- MLP branch
-        dyb = self._scaled(dxb, t['s2'], b, l)
-        dh = self.fc2.bwd(dyb, t['h'], sink)
-        du = ops.gelu_bwd(dh, t['u'])
+        # ---- MLP branch: fc2 data gradient comes out already multiplied by gelu'(u)
+        du = self.fc2.bwd(dxb, t['h'], sink, gelu_pre=t['u'])
         dln2 = self.fc1.bwd(du, t['ln2'], sink)
-        dx, dxb = self._ln_bwd(blk.norm2, dln2, t['x_mid'], t['st2'], dx, sink)
+        dx, dxb = self._ln_bwd(blk.norm2, dln2, t['x_mid'], t['st2'], dx, sink, t['s1'], l)
         # ---- attention branch
-        dyb = self._scaled(dxb, t['s1'], b, l)
-        datt = self.proj.bwd(dyb, t['att'], sink)
+        datt = self.proj.bwd(dxb, t['att'], sink)
         dqkv = ops.attention_bwd(t['qkv'], t['att'], datt, t['lse'], b, l, self.heads, d, self.scale)
         dln1 = self.qkv.bwd(dqkv, t['ln1'], sink)
-        return self._ln_bwd(blk.norm1, dln1, t['x_in'], t['st1'], dx, sink)
+        return self._ln_bwd(blk.norm1, dln1, t['x_in'], t['st1'], dx, sink, next_scale, l)
 
 
 class ViTRT:
@@ -208,7 +196,7 @@ class ViTRT:
         self.tape = tape if keep_tape else None
         return logits
 
-    def head_backward(self, dlogits, tape):
+    def head_backward(self, dlogits, tape, next_scale=None):
         m, sink = self.model, self.sink
         b, l, c = tape['b'], tape['l'], m.embedding_planes
         ncls = m.fc.weight.shape[0]
@@ -226,7 +214,7 @@ class ViTRT:
         sink.done(m.norm.weight, gbuf)
         sink.done(m.norm.bias, nbuf)
         dxb = torch.empty(b * l, c, device=dl.device, dtype=torch.bfloat16)
-        dx = ops.token_pool_bwd(dpooled, l, m.global_pool, dx_bf16=dxb.view(b, l, c))
+        dx = ops.token_pool_bwd(dpooled, l, m.global_pool, dx_bf16=dxb.view(b, l, c), bf16_row_scale=next_scale)
         return dx.view(b * l, c), dxb
 
     def _fc_bwd_nobias(self, dl, x):
@@ -267,9 +255,11 @@ class ViTRT:
         tape, sink = self.tape, self.sink
         assert tape is not None, 'backward called without a training forward'
         self.tape = None
-        dx, dxb = self.head_backward(dlogits, tape)
-        for blk, t in zip(reversed(self.blocks), reversed(tape['blocks'])):
-            dx, dxb = blk.backward(dx, dxb, t, tape['b'], tape['l'], sink)
+        tapes = tape['blocks']
+        dx, dxb = self.head_backward(dlogits, tape, next_scale=tapes[-1]['s2'] if tapes else None)
+        for i in range(len(self.blocks) - 1, -1, -1):
+            nxt = tapes[i - 1]['s2'] if i > 0 else None
+            dx, dxb = self.blocks[i].backward(dx, dxb, tapes[i], tape['b'], tape['l'], sink, next_scale=nxt)
         self.embed_backward(dx, tape)
         if sink.on_backward_end is not None:
             sink.on_backward_end()

@@ -34,25 +34,27 @@ def make_conv_shape(n, h, w, c, k, r, s, stride, pad):
 
 
 # ----------------------------------------------------------------------------- dense layers
-def linear_fwd(x, w, bias=None, resid=None, out=None, flags=0, out_f32=False):
+def linear_fwd(x, w, bias=None, resid=None, out=None, flags=0, out_f32=False, row_scale=None, rows_per_scale=0):
+    """row_scale: fp32 [M // rows_per_scale] drop-path scale applied to (x w^T + bias) before +resid."""
     M, K = x.shape
     N = w.shape[0]
     assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == K
     if out is None:
         out = torch.empty(M, N, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
-    _lib.call('saicv_linear_fwd', _p(x), _p(w), _p(bias), _p(resid), _p(out), M, N, K, flags,
-              int(out_f32), _stream())
+    _lib.call('saicv_linear_fwd', _p(x), _p(w), _p(bias), _p(resid), _p(row_scale), rows_per_scale, _p(out),
+              M, N, K, flags, int(out_f32), _stream())
     return out
 
 
-def linear_dgrad(dy, w, resid=None, out=None, flags=0, out_f32=False):
+def linear_dgrad(dy, w, resid=None, out=None, flags=0, out_f32=False, gelu_pre=None):
+    """gelu_pre: bf16 [M, K] pre-activation; the result is multiplied by gelu'(gelu_pre) in the epilogue."""
     M, N = dy.shape
     K = w.shape[1]
     assert dy.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[0] == N
     if out is None:
         out = torch.empty(M, K, device=dy.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
-    _lib.call('saicv_linear_dgrad', _p(dy), _p(w), _p(resid), _p(out), M, N, K, flags, int(out_f32),
-              _stream())
+    _lib.call('saicv_linear_dgrad', _p(dy), _p(w), _p(resid), _p(gelu_pre), _p(out), M, N, K, flags,
+              int(out_f32), _stream())
     return out
 
 
@@ -275,13 +277,14 @@ def layernorm_fwd(x, gamma, beta, eps, out=None, stats=None):
     return out, stats
 
 
-def layernorm_bwd(dy, x, gamma, stats, dgamma, dbeta, dres=None, dx=None, dx_bf16=None, accumulate=False):
+def layernorm_bwd(dy, x, gamma, stats, dgamma, dbeta, dres=None, dx=None, dx_bf16=None, accumulate=False,
+                  bf16_row_scale=None, rows_per_scale=0):
     rows, c = x.numel() // x.shape[-1], x.shape[-1]
     assert dy.dtype == torch.bfloat16 and x.dtype == torch.float32
     if dx is None:
         dx = torch.empty(x.shape, device=x.device, dtype=torch.float32)
     _lib.call('saicv_layernorm_bwd', _p(dy), _p(x), _p(gamma), _p(stats), _p(dres), _p(dx), _p(dx_bf16),
-              _p(dgamma), _p(dbeta), rows, c, int(accumulate), _stream())
+              _p(bf16_row_scale), rows_per_scale, _p(dgamma), _p(dbeta), rows, c, int(accumulate), _stream())
     return dx
 
 
@@ -321,11 +324,12 @@ def token_pool_fwd(x, mean_pool, out=None):
     return out
 
 
-def token_pool_bwd(dpooled, l, mean_pool, dx=None, dx_bf16=None):
+def token_pool_bwd(dpooled, l, mean_pool, dx=None, dx_bf16=None, bf16_row_scale=None):
     b, c = dpooled.shape
     if dx is None:
         dx = torch.empty(b, l, c, device=dpooled.device, dtype=torch.float32)
-    _lib.call('saicv_token_pool_bwd', _p(dpooled), _p(dx), _p(dx_bf16), b, l, c, int(mean_pool), _stream())
+    _lib.call('saicv_token_pool_bwd', _p(dpooled), _p(dx), _p(dx_bf16), _p(bf16_row_scale), b, l, c,
+              int(mean_pool), _stream())
     return dx
 
 

@@ -58,6 +58,22 @@ def test_linear_fwd_gelu_resid():
     _close(y, x.float() @ w.float().t() + bias + resid, 1e-4, 1e-4, 'residual epilogue')
 
 
+def test_linear_epilogue_rowscale_and_dgelu():
+    ops = _ops()
+    M, N, K, L = 6 * 50, 256, 128, 50
+    x, w = _bf(M, K, seed=1), _bf(N, K, scale=K ** -0.5, seed=2)
+    bias, resid = torch.randn(N, device='cuda'), torch.randn(M, N, device='cuda')
+    rs = torch.tensor([0., 1.25, 1.25, 0., 1.25, 1.25], device='cuda')
+    y = ops.linear_fwd(x, w, bias=bias, resid=resid, out_f32=True, row_scale=rs, rows_per_scale=L)
+    ref = resid + rs.repeat_interleave(L)[:, None] * (x.float() @ w.float().t() + bias)
+    _close(y, ref, 1e-4, 1e-4, 'row-scaled residual epilogue')
+    dy, u = _bf(M, N, seed=3), _bf(M, K, scale=2.0, seed=4)
+    dx = ops.linear_dgrad(dy, w, gelu_pre=u)
+    uf = u.float().requires_grad_(True)
+    F.gelu(uf).backward(dy.float() @ w.float())
+    _close(dx, uf.grad, 1e-2, 1e-2, 'dgelu epilogue')
+
+
 @pytest.mark.parametrize('M,N,K', [(256, 128, 64), (300, 1000, 2048), (1024, 3072, 768)])
 def test_linear_dgrad(M, N, K):
     ops = _ops()
