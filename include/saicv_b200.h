@@ -37,8 +37,12 @@ long long saicv_launch_count(void);
  * or fp32 (out_f32); bias [N] fp32, resid [M,N] fp32 and row_scale (drop-path, vit.py:118-135) may
  * be NULL. */
 int saicv_linear_fwd(const void* x, const void* w, const float* bias, const float* resid,
-                     const float* row_scale, int rows_per_scale, void* y, int M, int N, int K,
-                     int flags, int out_f32, void* stream);
+                     const float* row_scale, int rows_per_scale, float* stats_partial, void* y,
+                     int M, int N, int K, int flags, int out_f32, void* stream);
+/* Forward GEMMs (saicv_linear_fwd / saicv_conv_fprop) can accumulate the BatchNorm statistics of
+ * their own (bf16) output in the epilogue: pass stats_partial (saicv_gemm_stats_rows(M, N) * 2 * N
+ * floats, <= SAICV_BN_PARTIAL_ROWS rows) and hand it to saicv_bn_finalize with that row count. */
+int saicv_gemm_stats_rows(long long out_rows, int out_cols);
 /* dx[M,K] = (dy[M,N] w[N,K]) (* gelu'(gelu_pre[M,K])) (+ resid[M,K]); dy,w,gelu_pre bf16; dx bf16
  * or fp32; gelu_pre (the pre-activation saved by the forward, vit.py:87-89) and resid may be NULL. */
 int saicv_linear_dgrad(const void* dy, const void* w, const float* resid, const void* gelu_pre,
@@ -57,8 +61,8 @@ typedef struct {
 } saicv_conv_shape;
 /* y[n,p,q,k] bf16; requires c % 64 == 0 (the 3-channel stem goes through saicv_stem_im2col +
  * saicv_linear_fwd). */
-int saicv_conv_fprop(const void* x, const void* w, void* y, const saicv_conv_shape* cs, int flags,
-                     void* stream);
+int saicv_conv_fprop(const void* x, const void* w, float* stats_partial, void* y,
+                     const saicv_conv_shape* cs, int flags, void* stream);
 /* dx[n,h,w,c] = sum dy[n, h+pad-r, w+pad-s, k] w[k,r,s,c] (+ add[n,h,w,c]): stride-1 data
  * gradient; `add` (bf16, may be NULL) is the gradient arriving over the shortcut, fused into the
  * epilogue.  For a stride-2 conv pass the zero-upsampled dy (saicv_zero_upsample2) and stride = 1.
@@ -72,13 +76,15 @@ int saicv_conv_wgrad(const void* dy, const void* x, float* dw_partial, const sai
 /* ---- layout / weight preparation ---------------------------------------------------------- */
 /* fp32 [k][c][r][s] (torch Conv2d.weight) -> bf16 [k][kpad], zero padded to kpad (kpad >=
  * r*s*c, multiple of 8).  order 0: column (r*S+s)*C + c, the implicit-GEMM layout of
- * saicv_conv_*; order 1: column (c*R+r)*S + s, the layout of saicv_stem_im2col. */
+ * saicv_conv_*; order 1: column (c*R+r)*S + s, the layout of saicv_stem_im2col.  kp / cp (0 = k / c):
+ * rows and per-tap channels padded with zeros (networks whose channel counts are not multiples of
+ * 64 run on channel-padded activations, e.g. DarkNet's 32-channel stem). */
 int saicv_prep_conv_weight(const float* w, void* w_bf16, int k, int c, int r, int s, int kpad,
-                           int order, void* stream);
+                           int order, int kp, int cp, void* stream);
 /* sum of fp32 partials [splits][k][kpad] (columns in `order`) -> fp32 grad in torch layout
  * [k][c][r][s]; accumulate != 0 adds to the destination (gradient accumulation). */
 int saicv_finish_conv_wgrad(const float* partial, float* grad, int splits, int k, int c, int r,
-                            int s, int kpad, int accumulate, int order, void* stream);
+                            int s, int kpad, int accumulate, int order, int kp, int cp, void* stream);
 /* out[i] (+)= sum_s partial[s][i]; plain reduction for linear wgrad. */
 int saicv_reduce_partials(const float* partial, float* out, int splits, long long n,
                           int accumulate, void* stream);
@@ -104,14 +110,16 @@ int saicv_add_strided2(void* dx, const void* dd, int n, int p, int q, int h, int
 #define SAICV_BN_PARTIAL_ROWS 296
 /* per-channel partial sum / sum of squares of y[rows][c] (bf16) -> partials. */
 int saicv_bn_stats(const void* y, float* partials, long long rows, int c, void* stream);
-/* folds `partials` (from saicv_bn_stats with the same rows, c) -> mean/var -> scale_shift[2][c],
- * saved[2][c] = (mean, rstd); running stats updated with `momentum` and the unbiased variance
- * exactly like nn.BatchNorm2d (running_* may be NULL). */
-int saicv_bn_finalize(const float* partials, const float* gamma, const float* beta,
+/* folds `partial_rows` rows of `partials` (0: the row count saicv_bn_stats used for this rows, c;
+ * otherwise the count returned by saicv_gemm_stats_rows for an epilogue-fused reduction) ->
+ * mean/var -> scale_shift[2][c], saved[2][c] = (mean, rstd); running stats updated with `momentum`
+ * and the unbiased variance exactly like nn.BatchNorm2d (running_* may be NULL). */
+int saicv_bn_finalize(const float* partials, int partial_rows, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, float* scale_shift, float* saved,
                       long long rows, int c, float eps, float momentum, void* stream);
 /* out = act(y*scale+shift + res) ; res optional, itself optionally batch-normalised with
- * res_scale_shift (downsample branch).  act: 0 none, 1 ReLU, 2 LeakyReLU(0.1). */
+ * res_scale_shift (downsample branch).  act: 0 none, 1 ReLU, 2 LeakyReLU(0.1); act | 8: the
+ * residual is added after the activation, out = act(y*scale+shift) + res (darknet.py:141-144). */
 int saicv_bn_apply(const void* y, const float* scale_shift, const void* res,
                    const float* res_scale_shift, void* out, long long rows, int c, int act,
                    void* stream);

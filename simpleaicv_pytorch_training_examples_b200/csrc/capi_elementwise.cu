@@ -205,20 +205,22 @@ colreduce_kernel(const void* __restrict__ a, const void* __restrict__ b, const v
   }
 }
 
-// out[j] (+)= sum_b partial[b][j]: 32 columns x 8 row groups per block
+// out[j] (+)= sum_b partial[b][j]: 8 columns x 32 row groups per block (the <= 296 partial rows are
+// spread over 32 threads per column so the fold is a handful of loads deep)
 __global__ void fold_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblk, int ncols,
                                      int accumulate) {
-  __shared__ float sm[8][33];
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31), grp = threadIdx.x >> 5;
+  __shared__ float sm[32][9];
+  const int cl = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  const int col = blockIdx.x * 8 + cl;
   float s = 0.f;
   if (col < ncols)
-    for (int b = grp; b < nblk; b += 8) s += partial[(long long)b * ncols + col];
-  sm[grp][threadIdx.x & 31] = s;
+    for (int b = grp; b < nblk; b += 32) s += partial[(long long)b * ncols + col];
+  sm[grp][cl] = s;
   __syncthreads();
   if (grp == 0 && col < ncols) {
     float t = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) t += sm[g][threadIdx.x];
+    for (int g = 0; g < 32; ++g) t += sm[g][cl];
     out[col] = accumulate ? out[col] + t : t;
   }
 }
@@ -263,7 +265,7 @@ int partial_rows(long long rows, int C) {  // must mirror launch_colreduce<0>
   return n;
 }
 int fold(const float* partials, float* out, int nblk, int ncols, int accumulate, cudaStream_t st) {
-  fold_partials_kernel<<<(ncols + 31) / 32, 256, 0, st>>>(partials, out, nblk, ncols, accumulate);
+  fold_partials_kernel<<<(ncols + 7) / 8, 256, 0, st>>>(partials, out, nblk, ncols, accumulate);
   return check_launch("fold_partials_kernel");
 }
 
@@ -278,30 +280,30 @@ __global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict
 }
 
 // ----------------------------------------------------------------------------- BN finalize
-// Folds the per-block partial sums (deterministic order) and finalises 32 channels per block.
+// Folds the per-block partial sums (deterministic order) and finalises 8 channels per block.
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblk, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ rmean,
                                    float* __restrict__ rvar, float* __restrict__ ss,
                                    float* __restrict__ saved, long long rows, int C, float eps,
                                    float momentum) {
-  __shared__ float sm[2][8][33];
-  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
+  __shared__ float sm[2][32][9];
+  const int cl = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   float s0 = 0.f, s1 = 0.f;
   if (c < C)
-    for (int b = grp; b < nblk; b += 8) {
+    for (int b = grp; b < nblk; b += 32) {
       s0 += partials[(long long)b * 2 * C + c];
       s1 += partials[(long long)b * 2 * C + C + c];
     }
-  sm[0][grp][lane] = s0;
-  sm[1][grp][lane] = s1;
+  sm[0][grp][cl] = s0;
+  sm[1][grp][cl] = s1;
   __syncthreads();
   if (grp != 0 || c >= C) return;
   s0 = s1 = 0.f;
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    s0 += sm[0][g][lane];
-    s1 += sm[1][g][lane];
+  for (int g = 0; g < 32; ++g) {
+    s0 += sm[0][g][cl];
+    s1 += sm[1][g][cl];
   }
   const float inv_n = 1.0f / (float)rows;
   const float mean = s0 * inv_n;
@@ -360,14 +362,21 @@ bn_apply_kernel(const void* __restrict__ y, const float* __restrict__ ss, const 
       unpack8(vy[u], f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = f[i] * sc[i] + sh[i];
+      const bool res_after = (act & 8) != 0;  // DarkNet: act(bn(y)) + res; ResNet: act(bn(y) + res)
+      if (res_after) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = act_apply(f[i], act & 7);
+      }
       if (HAS_RES) {
         float rv[8];
         unpack8(vr[u], rv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] += RES_BN ? rv[i] * rsc[i] + rsh[i] : rv[i];
       }
+      if (!res_after) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = act_apply(f[i], act);
+        for (int i = 0; i < 8; ++i) f[i] = act_apply(f[i], act);
+      }
       stg8(out, (r + (long long)u * gm.ty_count) * vpr + tx, pack8(f));
     }
   }
@@ -483,21 +492,22 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, float*
   }
 }
 
-// order 0: column (r*S+s)*C + c (implicit-GEMM convs); order 1: column (c*R+r)*S + s (= torch
-// layout, used by the explicit im2col of 3-channel stems / patch embeddings)
+// order 0: column (r*S+s)*Cp + c (implicit-GEMM convs, Cp = channels padded to the GEMM granule);
+// order 1: column (c*R+r)*S + s (= torch layout, used by the explicit im2col of 3-channel stems /
+// patch embeddings).  Rows k >= K and channels c >= C are zero (channel padding).
 __global__ void prep_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int K, int C,
-                                        int R, int S, int kpad, int order) {
-  const long long total = (long long)K * kpad;
+                                        int R, int S, int kpad, int order, int Kp, int Cp) {
+  const long long total = (long long)Kp * kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i / kpad), j = (int)(i % kpad);
     float v = 0.f;
-    if (j < R * S * C) {
+    if (k < K) {
       if (order == 1) {
-        v = w[(long long)k * C * R * S + j];
-      } else {
-        const int tap = j / C, c = j % C;
-        v = w[((long long)k * C + c) * (R * S) + tap];
+        if (j < R * S * C) v = w[(long long)k * C * R * S + j];
+      } else if (j < R * S * Cp) {
+        const int tap = j / Cp, c = j % Cp;
+        if (c < C) v = w[((long long)k * C + c) * (R * S) + tap];
       }
     }
     o[i] = __float2bfloat16_rn(v);
@@ -505,7 +515,8 @@ __global__ void prep_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
 }
 
 __global__ void finish_conv_wgrad_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits,
-                                         int K, int C, int R, int S, int kpad, int accumulate, int order) {
+                                         int K, int C, int R, int S, int kpad, int accumulate, int order, int Kp,
+                                         int Cp) {
   const long long total = (long long)K * C * R * S;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -513,9 +524,9 @@ __global__ void finish_conv_wgrad_kernel(const float* __restrict__ partial, floa
     const long long kc = i / (R * S);
     const int c = (int)(kc % C), k = (int)(kc / C);
     const long long src = order == 1 ? (long long)k * kpad + (i - (long long)k * C * R * S)
-                                     : (long long)k * kpad + (long long)tap * C + c;
+                                     : (long long)k * kpad + (long long)tap * Cp + c;
     float s = accumulate ? grad[i] : 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += partial[(long long)sp * K * kpad + src];
+    for (int sp = 0; sp < splits; ++sp) s += partial[(long long)sp * Kp * kpad + src];
     grad[i] = s;
   }
 }
@@ -748,10 +759,11 @@ int saicv_bn_stats(const void* y, float* partials, long long rows, int c, void* 
   return launch_colreduce<0>(y, nullptr, nullptr, nullptr, nullptr, partials, rows, c, 0, &nblk, ST);
 }
 
-int saicv_bn_finalize(const float* partials, const float* gamma, const float* beta, float* running_mean,
-                      float* running_var, float* scale_shift, float* saved, long long rows, int c,
-                      float eps, float momentum, void* stream) {
-  bn_finalize_kernel<<<(c + 31) / 32, 256, 0, ST>>>(partials, partial_rows(rows, c), gamma, beta, running_mean,
+int saicv_bn_finalize(const float* partials, int partial_rows_, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float* scale_shift, float* saved, long long rows,
+                      int c, float eps, float momentum, void* stream) {
+  const int nrows = partial_rows_ > 0 ? partial_rows_ : partial_rows(rows, c);
+  bn_finalize_kernel<<<(c + 7) / 8, 256, 0, ST>>>(partials, nrows, gamma, beta, running_mean,
                                                     running_var, scale_shift, saved, rows, c, eps, momentum);
   return check_launch("bn_finalize_kernel");
 }
@@ -820,17 +832,22 @@ int saicv_reduce_partials(const float* partial, float* out, int splits, long lon
 }
 
 int saicv_prep_conv_weight(const float* w, void* w_bf16, int k, int c, int r, int s, int kpad, int order,
-                           void* stream) {
-  if (kpad % 8 || kpad < r * s * c) return set_error("saicv_prep_conv_weight: bad kpad %d", kpad);
-  prep_conv_weight_kernel<<<grid_for((long long)k * kpad), kThreads, 0, ST>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(w_bf16), k, c, r, s, kpad, order);
+                           int kp, int cp, void* stream) {
+  if (kp <= 0) kp = k;
+  if (cp <= 0) cp = c;
+  if (kpad % 8 || kpad < r * s * (order == 1 ? c : cp) || kp < k || cp < c)
+    return set_error("saicv_prep_conv_weight: bad padding (kpad %d kp %d cp %d)", kpad, kp, cp);
+  prep_conv_weight_kernel<<<grid_for((long long)kp * kpad), kThreads, 0, ST>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(w_bf16), k, c, r, s, kpad, order, kp, cp);
   return check_launch("prep_conv_weight_kernel");
 }
 
 int saicv_finish_conv_wgrad(const float* partial, float* grad, int splits, int k, int c, int r, int s, int kpad,
-                            int accumulate, int order, void* stream) {
+                            int accumulate, int order, int kp, int cp, void* stream) {
+  if (kp <= 0) kp = k;
+  if (cp <= 0) cp = c;
   finish_conv_wgrad_kernel<<<grid_for((long long)k * c * r * s), kThreads, 0, ST>>>(partial, grad, splits, k, c, r,
-                                                                                     s, kpad, accumulate, order);
+                                                                                     s, kpad, accumulate, order, kp, cp);
   return check_launch("finish_conv_wgrad_kernel");
 }
 

@@ -134,6 +134,12 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, con
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
   const long long total = (long long)num_m * num_n * p.splits;
   const int grid = (int)(total < g_sm_count ? total : g_sm_count);
+  // smem ring depth: everything that fits next to the store buffers (and the stats accumulators)
+  const int stat_bytes = (p.epi_flags & EPI_STATS) ? ((8 * p.N + 15) & ~15) : 0;
+  int stages = (kSmemBudget - 2 * kStoreBufBytes - stat_bytes) / Cfg::kStageBytes;
+  if (stages > Cfg::kStages) stages = Cfg::kStages;
+  if (stages < 2) return set_error("gemm_sm100_kernel<%d>: %d bytes of statistics do not fit in shared memory", BN, stat_bytes);
+  const_cast<GemmParams&>(p).num_stages = stages;
   gemm_sm100_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a, b, d, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm_sm100_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
@@ -172,6 +178,14 @@ extern "C" {
 
 int saicv_sm_count(void) { return ensure_init() ? g_sm_count : 0; }
 
+int saicv_gemm_stats_rows(long long out_rows, int out_cols) {
+  // number of partial rows a stats-fused forward GEMM writes = its grid size
+  const int bn = pick_bn(out_cols);
+  const long long tiles = ((out_rows + BM - 1) / BM) * ((out_cols + bn - 1) / bn);
+  const int sms = ensure_init() ? g_sm_count : 148;
+  return (int)(tiles < sms ? tiles : sms);
+}
+
 int saicv_wgrad_splits(int out_rows, int out_cols, long long reduce_len) {
   const int bn = pick_bn(out_cols);
   const long long tiles = (long long)((out_rows + BM - 1) / BM) * ((out_cols + bn - 1) / bn);
@@ -189,8 +203,8 @@ int saicv_wgrad_splits(int out_rows, int out_cols, long long reduce_len) {
 }
 
 int saicv_linear_fwd(const void* x, const void* w, const float* bias, const float* resid,
-                     const float* row_scale, int rows_per_scale, void* y, int M, int N, int K, int flags,
-                     int out_f32, void* stream) {
+                     const float* row_scale, int rows_per_scale, float* stats_partial, void* y, int M, int N,
+                     int K, int flags, int out_f32, void* stream) {
   if (!ensure_init()) return 1;
   if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (K % 8) || (N % (out_f32 ? 4 : 8)))
     return set_error("saicv_linear_fwd: unaligned operand (M=%d N=%d K=%d)", M, N, K);
@@ -207,6 +221,10 @@ int saicv_linear_fwd(const void* x, const void* w, const float* bias, const floa
                 (row_scale ? EPI_ROW_SCALE : 0);
   if (row_scale && rows_per_scale <= 0) return set_error("saicv_linear_fwd: rows_per_scale must be > 0");
   p.row_scale = row_scale; p.rows_per_scale = rows_per_scale;
+  if (stats_partial) {
+    if (bias || resid || out_f32) return set_error("saicv_linear_fwd: stats_partial needs a plain bf16 output (no bias / residual)");
+    p.epi_flags |= EPI_STATS; p.stats_partial = stats_partial;
+  }
   p.out_f32 = out_f32; p.bias = bias; p.resid = resid; p.out = y; p.ldd = N; p.split_stride = 0;
   return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream);
 }
@@ -256,8 +274,8 @@ int saicv_linear_wgrad(const void* dy, const void* x, float* dw_partial, int M, 
 
 static int conv_out(int in, int pad, int r, int stride) { return (in + 2 * pad - r) / stride + 1; }
 
-int saicv_conv_fprop(const void* x, const void* w, void* y, const saicv_conv_shape* cs, int flags,
-                     void* stream) {
+int saicv_conv_fprop(const void* x, const void* w, float* stats_partial, void* y, const saicv_conv_shape* cs,
+                     int flags, void* stream) {
   if (!ensure_init()) return 1;
   if (cs->c % 64 || cs->k % 8 || !aligned16(x) || !aligned16(w) || !aligned16(y))
     return set_error("saicv_conv_fprop: needs c%%64==0, k%%8==0 and 16B-aligned pointers (c=%d k=%d)", cs->c, cs->k);
@@ -276,7 +294,8 @@ int saicv_conv_fprop(const void* x, const void* w, void* y, const saicv_conv_sha
   p.a_mode = A_IM2COL; p.b_mode = B_K2D; p.b_cin = cs->c;
   p.g.P = P; p.g.Q = Q; p.g.stride = cs->stride; p.g.lc_h = -cs->pad; p.g.lc_w = -cs->pad;
   p.g.R = cs->r; p.g.S = cs->s; p.g.cchunks = cs->c / 64; p.g.n_img = cs->n;
-  p.epi_flags = flags & ~(EPI_BIAS | EPI_RESID); p.out_f32 = 0; p.out = y; p.ldd = cs->k;
+  p.epi_flags = flags & (EPI_RELU | EPI_DIRECT); p.out_f32 = 0; p.out = y; p.ldd = cs->k;
+  if (stats_partial) { p.epi_flags |= EPI_STATS; p.stats_partial = stats_partial; }
   return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream);
 }
 

@@ -24,7 +24,7 @@ namespace saicv {
 enum : int { A_K2D = 0, A_IM2COL = 1, A_MN2D = 2 };
 enum : int { B_K2D = 0, B_MN2D = 2, B_IM2COL = 3 };
 enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_GELU = 4, EPI_DIRECT = 8, EPI_RESID = 16, EPI_RESID_BF16 = 32,
-              EPI_MUL_DGELU = 64, EPI_ROW_SCALE = 128 };
+              EPI_MUL_DGELU = 64, EPI_ROW_SCALE = 128, EPI_STATS = 256 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -71,6 +71,8 @@ struct GemmParams {
   void* out;           // direct-store path
   long long ldd;       // leading dimension of D in elements
   long long split_stride;  // elements between split-K partial outputs
+  int num_stages;      // smem ring depth actually used (<= GemmCfg::kStages)
+  float* stats_partial;  // EPI_STATS: [gridDim.x][2][N] per-CTA column sums / sums of squares of the bf16 output
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -92,10 +94,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int nstages = p.num_stages;
+  const bool do_stats = (p.epi_flags & EPI_STATS) != 0;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kABytes;
-  uint8_t* sD = smem + kStages * Cfg::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sD + 2 * kStoreBufBytes);
+  uint8_t* sB = smem + nstages * kABytes;
+  uint8_t* sD = smem + nstages * Cfg::kStageBytes;
+  float* sStat = reinterpret_cast<float*>(sD + 2 * kStoreBufBytes);  // [2][N] when EPI_STATS
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sD + 2 * kStoreBufBytes + (do_stats ? ((8 * p.N + 15) & ~15) : 0));
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -208,7 +213,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                  (uint16_t)(valid ? rj : 0));
             }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -245,7 +250,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             umma_bf16(d_tmem, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
@@ -272,6 +277,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int split_at = p.out_f32 ? (NCH + 1) / 2 : 2 * ((BN / 64 + 1) / 2);
     const int c_begin = half ? split_at : 0;
     const int c_end = half ? NCH : split_at;
+    if (do_stats) {
+      for (int j = threadIdx.x - 128; j < 2 * p.N; j += 256) sStat[j] = 0.f;
+      named_bar_sync(3, 256);
+    }
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int n_blk = w % num_n;
       const int t = w / num_n;
@@ -361,6 +370,33 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         }
+        if (do_stats) {
+          // per-column sum / sum of squares of the values as they are stored (bf16-rounded): a
+          // 31-shuffle transpose-reduce leaves column col0+lane's total over this warp's 32 rows in
+          // lane `lane`; rows beyond M and columns beyond N hold exact zeros (TMA zero fill).
+          float sx[32], sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float r = __bfloat162float(__float2bfloat16_rn(f[j]));
+            sx[j] = r;
+            sq[j] = r * r;
+          }
+#pragma unroll
+          for (int o = 16, n = 16; o >= 1; o >>= 1, n >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              const float send_x = up ? sx[i] : sx[i + n], keep_x = up ? sx[i + n] : sx[i];
+              const float send_q = up ? sq[i] : sq[i + n], keep_q = up ? sq[i + n] : sq[i];
+              sx[i] = keep_x + __shfl_xor_sync(0xffffffffu, send_x, o);
+              sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, o);
+            }
+          }
+          if (col0 + lane < p.N) {
+            atomicAdd(&sStat[col0 + lane], sx[0]);
+            atomicAdd(&sStat[p.N + col0 + lane], sq[0]);
+          }
+        }
         if (direct) {
           if (row < p.M) {
             if (p.out_f32) {
@@ -434,6 +470,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (gtid == 0) tma_store_wait<0>();
+    if (do_stats) {
+      named_bar_sync(3, 256);
+      float* dst = p.stats_partial + (long long)blockIdx.x * 2 * p.N;
+      for (int j = threadIdx.x - 128; j < 2 * p.N; j += 256) dst[j] = sStat[j];
+    }
   }
 
   tc_fence_before();

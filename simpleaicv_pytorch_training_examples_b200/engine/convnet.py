@@ -20,6 +20,8 @@ import torch
 from .. import ops
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+# BatchNorm batch statistics are accumulated by the conv GEMM's epilogue instead of a separate pass over y
+FUSE_BN_STATS = True
 
 
 def _round_up(v, m):
@@ -58,21 +60,29 @@ class GradSink:
 
 
 class ConvBN:
-    """Runtime state of one ConvBnActBlock: conv (no bias) -> BatchNorm2d -> activation."""
+    """Runtime state of one ConvBnActBlock: conv (no bias) -> BatchNorm2d -> activation.
 
-    def __init__(self, block, act):
+    Channel counts that are not multiples of 64 (DarkNet's 32-channel layers) run on channel-padded
+    activations: filters k..kp-1 and input channels c..cp-1 of the bf16 operand copy are zero, so the
+    padded channels stay exactly zero through conv, BatchNorm (shift 0) and the activation, and carry
+    zero gradients; parameters, statistics and gradients exposed to torch keep their real sizes."""
+
+    def __init__(self, block, act, res_after_act=False):
         self.conv = block.layer[0]
         self.bn = block.layer[1]
         self.act = act
+        self.res_after_act = res_after_act
         k, c, r, s = self.conv.weight.shape
         self.k, self.c, self.r, self.s = k, c, r, s
         self.stride = self.conv.stride[0]
         self.pad = self.conv.padding[0]
         assert self.conv.groups == 1 and self.conv.bias is None and r == s
         assert self.conv.stride[0] == self.conv.stride[1] and self.conv.padding[0] == self.conv.padding[1]
-        assert k % 8 == 0, 'output channels must be a multiple of 8'
-        self.is_stem = (c % 64) != 0
-        self.kpad = _round_up(r * s * c, 64) if self.is_stem else r * s * c
+        self.is_stem = (c % 8) != 0            # 3-channel image input: explicit im2col from NCHW fp32
+        self.kp = _round_up(k, 64)
+        self.cp = c if self.is_stem else _round_up(c, 64)
+        self.padded = self.kp != k
+        self.kpad = _round_up(r * s * c, 64) if self.is_stem else r * s * self.cp
         self.w_bf16 = None
         self.w_version = None
         self.ss = None
@@ -82,67 +92,104 @@ class ConvBN:
     # ---- parameters
     def prep(self):
         w = self.conv.weight
+        bn = self.bn
         if self.w_bf16 is None or self.w_bf16.device != w.device:
             dev = w.device
-            self.w_bf16 = torch.empty(self.k, self.kpad, device=dev, dtype=torch.bfloat16)
-            self.ss = torch.empty(2, self.k, device=dev)
-            self.saved = torch.empty(2, self.k, device=dev)
-            self.sums = torch.zeros(2, self.k, device=dev)
+            self.w_bf16 = torch.empty(self.kp, self.kpad, device=dev, dtype=torch.bfloat16)
+            self.ss = torch.zeros(2, self.kp, device=dev)
+            self.saved = torch.empty(2, self.kp, device=dev)
+            self.sums = torch.zeros(2, self.kp, device=dev)
+            if self.padded:
+                self.gamma_p = torch.ones(self.kp, device=dev)
+                self.beta_p = torch.zeros(self.kp, device=dev)
+                self.rm_p = torch.zeros(self.kp, device=dev)
+                self.rv_p = torch.ones(self.kp, device=dev)
+                self.dg_p = torch.empty(self.kp, device=dev)
+                self.db_p = torch.empty(self.kp, device=dev)
             self.w_version = None
         ver = (w.data_ptr(), w._version)
         if ver != self.w_version:
             ops.prep_conv_weight(w.detach(), self.w_bf16, self.kpad,
-                                 order=ops.ORDER_CRS if self.is_stem else ops.ORDER_RSC)
+                                 order=ops.ORDER_CRS if self.is_stem else ops.ORDER_RSC, kp=self.kp, cp=self.cp)
             self.w_version = ver
+        if self.padded:
+            self.gamma_p[:self.k].copy_(bn.weight.detach())
+            self.beta_p[:self.k].copy_(bn.bias.detach())
+
+    def _gamma(self):
+        return self.gamma_p if self.padded else self.bn.weight.detach()
+
+    def _beta(self):
+        return self.beta_p if self.padded else self.bn.bias.detach()
 
     # ---- forward
     def out_hw(self, h, w):
         return (ops.conv_out_size(h, self.pad, self.r, self.stride),
                 ops.conv_out_size(w, self.pad, self.s, self.stride))
 
-    def conv_fwd(self, a_in, tape):
-        """a_in: NHWC bf16 activation, or the NCHW fp32 image batch for the stem."""
+    def conv_fwd(self, a_in, tape, want_stats=False):
+        """a_in: NHWC bf16 activation (cp channels), or the NCHW fp32 image batch for the stem.
+        want_stats: the GEMM epilogue also accumulates the BatchNorm statistics of its output."""
         if self.is_stem:
             n, _, h, w = a_in.shape
-            P, Q = self.out_hw(h, w)
+        else:
+            n, h, w, cin = a_in.shape
+            assert cin == self.cp, f'expected {self.cp} (padded) input channels, got {cin}'
+        P, Q = self.out_hw(h, w)
+        rows = n * P * Q
+        stats = ops.partial_ws(a_in.device, 2 * self.kp) if want_stats else None
+        tape['stats'] = (stats, ops.gemm_stats_rows(rows, self.kp)) if want_stats else None
+        if self.is_stem:
             cols = ops.stem_im2col(a_in, self.r, self.s, self.stride, self.pad, self.kpad)
-            y = ops.linear_fwd(cols, self.w_bf16).view(n, P, Q, self.k)
+            y = ops.linear_fwd(cols, self.w_bf16, stats=stats).view(n, P, Q, self.kp)
             tape['cols'] = cols
         else:
-            n, h, w, _ = a_in.shape
-            cs = ops.make_conv_shape(n, h, w, self.c, self.k, self.r, self.s, self.stride, self.pad)
-            y = ops.conv_fprop(a_in, self.w_bf16, cs)
+            cs = ops.make_conv_shape(n, h, w, self.cp, self.kp, self.r, self.s, self.stride, self.pad)
+            y = ops.conv_fprop(a_in, self.w_bf16, cs, stats=stats)
             tape['a_in'] = a_in
             tape['cs'] = cs
         tape['in_hw'] = (h, w)
         tape['y'] = y
         return y
 
-    def bn_prepare(self, y, training):
+    def bn_prepare(self, y, training, tape=None):
         """Fills self.ss (scale/shift) from batch statistics (training) or running stats (eval)."""
         bn = self.bn
-        rows = y.numel() // self.k
-        if training or not bn.track_running_stats:
+        rows = y.numel() // self.kp
+        track = bn.track_running_stats
+        if training or not track:
             momentum = bn.momentum if bn.momentum is not None else 0.1
-            partials = ops.bn_stats(y)
-            ops.bn_finalize(partials, bn.weight.detach(), bn.bias.detach(),
-                            bn.running_mean if bn.track_running_stats else None,
-                            bn.running_var if bn.track_running_stats else None,
-                            self.ss, self.saved, rows, bn.eps, momentum)
-            if bn.track_running_stats and bn.num_batches_tracked is not None:
+            fused = tape.get('stats') if tape is not None else None
+            if fused is not None:
+                partials, prow = fused
+            else:
+                partials, prow = ops.bn_stats(y), 0
+            if self.padded and track:
+                self.rm_p[:self.k].copy_(bn.running_mean)
+                self.rv_p[:self.k].copy_(bn.running_var)
+            rm = (self.rm_p if self.padded else bn.running_mean) if track else None
+            rv = (self.rv_p if self.padded else bn.running_var) if track else None
+            ops.bn_finalize(partials, self._gamma(), self._beta(), rm, rv, self.ss, self.saved, rows, bn.eps, momentum,
+                            partial_rows=prow)
+            if self.padded and track:
+                bn.running_mean.copy_(self.rm_p[:self.k])
+                bn.running_var.copy_(self.rv_p[:self.k])
+            if track and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked.add_(1)
         else:
             scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
-            self.ss[0].copy_(scale)
-            self.ss[1].copy_(bn.bias.detach() - bn.running_mean * scale)
+            self.ss.zero_()
+            self.ss[0, :self.k].copy_(scale)
+            self.ss[1, :self.k].copy_(bn.bias.detach() - bn.running_mean * scale)
 
     def forward(self, a_in, tape, training, res=None, res_unit=None):
-        """conv -> BN -> (+res) -> act.  res_unit: ConvBN whose BN is applied to `res` on the fly
-        (downsample branch)."""
-        y = self.conv_fwd(a_in, tape)
-        self.bn_prepare(y, training)
+        """conv -> BN -> (+res) -> act (or act then +res when res_after_act).  res_unit: ConvBN whose
+        BN is applied to `res` on the fly (downsample branch)."""
+        y = self.conv_fwd(a_in, tape, want_stats=training and FUSE_BN_STATS)
+        self.bn_prepare(y, training, tape)
         out = torch.empty_like(y)
-        ops.bn_apply(y, self.ss, out, self.act, res=res,
+        act = self.act | (8 if (self.res_after_act and res is not None) else 0)
+        ops.bn_apply(y, self.ss, out, act, res=res,
                      res_scale_shift=res_unit.ss if res_unit is not None else None)
         tape['out'] = out
         return out
@@ -152,7 +199,7 @@ class ConvBN:
         """dout: gradient w.r.t. the activated output.  Returns (dy, dres).
 
         The ReLU mask comes from `act_out` (block output, when a residual was added before the
-        activation) or, for plain conv->BN->ReLU units, is recomputed inside the kernels from
+        activation) or, for plain conv->BN->act units, is recomputed inside the kernels from
         sign(y*scale+shift), which saves reading the activated tensor twice."""
         act = self.act if act is None else act
         y = tape['y']
@@ -164,29 +211,39 @@ class ConvBN:
         gbuf, gacc = sink.begin(self.bn.weight)
         bbuf, bacc = sink.begin(self.bn.bias)
         assert gacc == bacc
-        ops.bn_bwd_apply(dout, mask_src, y, self.saved, self.bn.weight.detach(), self.sums, dy, dres,
-                         gbuf, bbuf, act, accumulate=gacc, scale_shift=ss)
+        if self.padded:
+            ops.bn_bwd_apply(dout, mask_src, y, self.saved, self.gamma_p, self.sums, dy, dres, self.dg_p, self.db_p,
+                             act, accumulate=False, scale_shift=ss)
+            if gacc:
+                gbuf.add_(self.dg_p[:self.k])
+                bbuf.add_(self.db_p[:self.k])
+            else:
+                gbuf.copy_(self.dg_p[:self.k])
+                bbuf.copy_(self.db_p[:self.k])
+        else:
+            ops.bn_bwd_apply(dout, mask_src, y, self.saved, self.bn.weight.detach(), self.sums, dy, dres,
+                             gbuf, bbuf, act, accumulate=gacc, scale_shift=ss)
         sink.done(self.bn.weight, gbuf)
         sink.done(self.bn.bias, bbuf)
         return dy, dres
 
     def conv_bwd(self, dy, tape, sink, need_dx=True, add=None):
-        """dy: gradient w.r.t. the raw conv output [n,P,Q,k].  Returns the data gradient
+        """dy: gradient w.r.t. the raw conv output [n,P,Q,kp].  Returns the data gradient
         (NHWC bf16, `add` fused in when given) or None.  A 1x1 stride-2 conv returns
-        ('strided', dd) with the compact gradient dd[n,P,Q,c] that belongs at the even pixels."""
+        ('strided', dd) with the compact gradient dd[n,P,Q,cp] that belongs at the even pixels."""
         w = self.conv.weight
         wbuf, wacc = sink.begin(w)
         n, P, Q, _ = dy.shape
         h, wd = tape['in_hw']
         if self.is_stem:
-            part = ops.linear_wgrad(dy.view(-1, self.k), tape['cols'])
-            ops.finish_conv_wgrad(part, wbuf, self.kpad, accumulate=wacc, order=ops.ORDER_CRS)
+            part = ops.linear_wgrad(dy.view(-1, self.kp), tape['cols'])
+            ops.finish_conv_wgrad(part, wbuf, self.kpad, accumulate=wacc, order=ops.ORDER_CRS, kp=self.kp)
             sink.done(w, wbuf)
             assert not need_dx, 'the stem has no data gradient'
             return None
         cs = tape['cs']
         part = ops.conv_wgrad(dy, tape['a_in'], cs)
-        ops.finish_conv_wgrad(part, wbuf, self.kpad, accumulate=wacc)
+        ops.finish_conv_wgrad(part, wbuf, self.kpad, accumulate=wacc, kp=self.kp, cp=self.cp)
         sink.done(w, wbuf)
         if not need_dx:
             return None
@@ -195,9 +252,9 @@ class ConvBN:
         assert self.stride == 2
         if self.r == 1:
             assert add is None
-            return 'strided', ops.linear_dgrad(dy.view(-1, self.k), self.w_bf16).view(n, P, Q, self.c)
+            return 'strided', ops.linear_dgrad(dy.view(-1, self.kp), self.w_bf16).view(n, P, Q, self.cp)
         u = ops.zero_upsample2(dy, h, wd)
-        cs1 = ops.make_conv_shape(n, h, wd, self.c, self.k, self.r, self.s, 1, self.pad)
+        cs1 = ops.make_conv_shape(n, h, wd, self.cp, self.kp, self.r, self.s, 1, self.pad)
         return ops.conv_dgrad(u, self.w_bf16, cs1, add=add)
 
 
@@ -223,8 +280,8 @@ class ResidualBlockRT:
         last, tl = self.units[-1], tapes[-1]
         if self.down is not None:
             td = tape.setdefault('d', dict())
-            yd = self.down.conv_fwd(a_in, td)
-            self.down.bn_prepare(yd, training)
+            yd = self.down.conv_fwd(a_in, td, want_stats=training and FUSE_BN_STATS)
+            self.down.bn_prepare(yd, training, td)
             out = last.forward(x, tl, training, res=yd, res_unit=self.down)
         else:
             out = last.forward(x, tl, training, res=a_in)
@@ -256,18 +313,63 @@ class ResidualBlockRT:
         return dx
 
 
-class ResNetRT:
-    """Whole-network runtime for ResNet (resnet.py:158-245) and ResNetCifar
-    (resnetforcifar.py:27-108): stem [+ maxpool] + 4 stages + avgpool + fc."""
+class PlainUnitRT:
+    """A single conv -> BN -> act unit used as a stage (DarkNet's strided 3x3 convs)."""
 
-    def __init__(self, model, has_maxpool):
+    def __init__(self, block, act):
+        self.unit = ConvBN(block, act)
+
+    def all_units(self):
+        return [self.unit]
+
+    def forward(self, a_in, tape, training):
+        return self.unit.forward(a_in, tape, training)
+
+    def backward(self, dout, tape, sink):
+        dy, _ = self.unit.bn_bwd(dout, tape, sink)
+        return self.unit.conv_bwd(dy, tape, sink)
+
+
+class DarkBlockRT:
+    """Darknet53Block (darknet.py:116-144): x + act(bn(conv3x3(act(bn(conv1x1(x)))))) — the shortcut is
+    added AFTER the activation, so the block gradient flows unmasked into the shortcut."""
+
+    def __init__(self, block, act):
+        self.u1 = ConvBN(block.conv[0], act)
+        self.u2 = ConvBN(block.conv[1], act, res_after_act=True)
+
+    def all_units(self):
+        return [self.u1, self.u2]
+
+    def forward(self, a_in, tape, training):
+        t1, t2 = tape.setdefault('u', [dict(), dict()])
+        return self.u2.forward(self.u1.forward(a_in, t1, training), t2, training, res=a_in)
+
+    def backward(self, dout, tape, sink):
+        t1, t2 = tape['u']
+        dy, _ = self.u2.bn_bwd(dout, t2, sink)          # mask of u2's own activation, recomputed from y
+        dx = self.u2.conv_bwd(dy, t2, sink)
+        dy, _ = self.u1.bn_bwd(dx, t1, sink)
+        dx = self.u1.conv_bwd(dy, t1, sink)
+        return ops.add_bf16(dx, dout)
+
+
+class ResNetRT:
+    """Whole-network runtime for the conv -> BN -> act classifiers: ResNet (resnet.py:158-245),
+    ResNetCifar (resnetforcifar.py:27-108) and Darknet53 (darknet.py:323-432): stem [+ maxpool] +
+    a sequence of stages + global average pool + fc."""
+
+    def __init__(self, model, has_maxpool, stem=None, blocks=None):
         self.model = model
         self.has_maxpool = has_maxpool
-        self.stem = ConvBN(model.conv1, ACT_RELU)
-        self.blocks = []
-        for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
-            for blk in layer:
-                self.blocks.append(ResidualBlockRT(blk))
+        if stem is None:
+            stem = ConvBN(model.conv1, ACT_RELU)
+            blocks = []
+            for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
+                for blk in layer:
+                    blocks.append(ResidualBlockRT(blk))
+        self.stem = stem
+        self.blocks = blocks
         self.fc = model.fc
         self.fc_w_bf16 = None
         self.fc_b_pad = None

@@ -34,15 +34,22 @@ def make_conv_shape(n, h, w, c, k, r, s, stride, pad):
 
 
 # ----------------------------------------------------------------------------- dense layers
-def linear_fwd(x, w, bias=None, resid=None, out=None, flags=0, out_f32=False, row_scale=None, rows_per_scale=0):
-    """row_scale: fp32 [M // rows_per_scale] drop-path scale applied to (x w^T + bias) before +resid."""
+def gemm_stats_rows(out_rows, out_cols):
+    return _lib.load().saicv_gemm_stats_rows(out_rows, out_cols)
+
+
+def linear_fwd(x, w, bias=None, resid=None, out=None, flags=0, out_f32=False, row_scale=None, rows_per_scale=0,
+               stats=None):
+    """row_scale: fp32 [M // rows_per_scale] drop-path scale applied to (x w^T + bias) before +resid.
+    stats: partial-sum workspace; the epilogue accumulates per-column sum / sum of squares of the
+    bf16 output into gemm_stats_rows(M, N) rows of it (hand both to bn_finalize)."""
     M, K = x.shape
     N = w.shape[0]
     assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == K
     if out is None:
         out = torch.empty(M, N, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
-    _lib.call('saicv_linear_fwd', _p(x), _p(w), _p(bias), _p(resid), _p(row_scale), rows_per_scale, _p(out),
-              M, N, K, flags, int(out_f32), _stream())
+    _lib.call('saicv_linear_fwd', _p(x), _p(w), _p(bias), _p(resid), _p(row_scale), rows_per_scale, _p(stats),
+              _p(out), M, N, K, flags, int(out_f32), _stream())
     return out
 
 
@@ -81,12 +88,12 @@ def reduce_partials(partial, out, accumulate=False):
 
 
 # ----------------------------------------------------------------------------- convolutions
-def conv_fprop(x, w, cs, out=None, flags=0):
+def conv_fprop(x, w, cs, out=None, flags=0, stats=None):
     P = conv_out_size(cs.h, cs.pad, cs.r, cs.stride)
     Q = conv_out_size(cs.w, cs.pad, cs.s, cs.stride)
     if out is None:
         out = torch.empty(cs.n, P, Q, cs.k, device=x.device, dtype=torch.bfloat16)
-    _lib.call('saicv_conv_fprop', _p(x), _p(w), _p(out), ctypes.byref(cs), flags, _stream())
+    _lib.call('saicv_conv_fprop', _p(x), _p(w), _p(stats), _p(out), ctypes.byref(cs), flags, _stream())
     return out
 
 
@@ -113,16 +120,17 @@ def conv_wgrad(dy, x, cs, partial=None):
 ORDER_RSC, ORDER_CRS = 0, 1  # K ordering of weight matrices: implicit GEMM / explicit im2col
 
 
-def prep_conv_weight(w_f32, out, kpad, order=ORDER_RSC):
+def prep_conv_weight(w_f32, out, kpad, order=ORDER_RSC, kp=0, cp=0):
+    """kp / cp: padded filter count / channels per tap of `out` (0: unpadded)."""
     k, c, r, s = w_f32.shape
-    _lib.call('saicv_prep_conv_weight', _p(w_f32), _p(out), k, c, r, s, kpad, order, _stream())
+    _lib.call('saicv_prep_conv_weight', _p(w_f32), _p(out), k, c, r, s, kpad, order, kp, cp, _stream())
     return out
 
 
-def finish_conv_wgrad(partial, grad, kpad, accumulate=False, order=ORDER_RSC):
+def finish_conv_wgrad(partial, grad, kpad, accumulate=False, order=ORDER_RSC, kp=0, cp=0):
     k, c, r, s = grad.shape
     _lib.call('saicv_finish_conv_wgrad', _p(partial), _p(grad), partial.shape[0], k, c, r, s, kpad,
-              int(accumulate), order, _stream())
+              int(accumulate), order, kp, cp, _stream())
     return grad
 
 
@@ -188,9 +196,10 @@ def bn_stats(y, partials=None):
     return partials
 
 
-def bn_finalize(stats, gamma, beta, rmean, rvar, scale_shift, saved, rows, eps, momentum):
+def bn_finalize(stats, gamma, beta, rmean, rvar, scale_shift, saved, rows, eps, momentum, partial_rows=0):
+    """partial_rows: 0 for partials written by bn_stats, else the row count of an epilogue-fused reduction."""
     c = gamma.numel()
-    _lib.call('saicv_bn_finalize', _p(stats), _p(gamma), _p(beta), _p(rmean), _p(rvar),
+    _lib.call('saicv_bn_finalize', _p(stats), partial_rows, _p(gamma), _p(beta), _p(rmean), _p(rvar),
               _p(scale_shift), _p(saved), rows, c, eps, momentum, _stream())
 
 

@@ -125,6 +125,24 @@ def test_conv_fprop(n, h, w, c, k, r, stride, pad):
     _close(y, ref, 1e-2, 1e-2, 'conv_fprop')
 
 
+@pytest.mark.parametrize('n,h,w,c,k,r,stride,pad', CONV_CASES + [(6, 14, 14, 256, 1024, 1, 1, 0), (3, 7, 7, 512, 2048, 1, 1, 0)])
+def test_conv_fprop_fused_bn_statistics(n, h, w, c, k, r, stride, pad):
+    """The GEMM epilogue's per-CTA column sums, folded by bn_finalize, equal the statistics of the
+    stored bf16 output (mean rtol 1e-3 / atol 1e-4, rstd rtol 1e-3)."""
+    ops, x_nchw, wt, x, wb, cs = _conv_case(n, h, w, c, k, r, stride, pad)
+    ws = ops.partial_ws(x.device, 2 * k)
+    y = ops.conv_fprop(x, wb, cs, stats=ws)
+    rows = y.numel() // k
+    gamma, beta = torch.ones(k, device='cuda'), torch.zeros(k, device='cuda')
+    ss, saved = torch.empty(2, k, device='cuda'), torch.empty(2, k, device='cuda')
+    ops.bn_finalize(ws, gamma, beta, None, None, ss, saved, rows, 1e-5, 0.1, partial_rows=ops.gemm_stats_rows(rows, k))
+    yf = y.float().view(rows, k)
+    _close(saved[0], yf.mean(0), 1e-3, 1e-4, 'fused mean')
+    _close(saved[1], torch.rsqrt(yf.var(0, unbiased=False) + 1e-5), 1e-3, 1e-4, 'fused rstd')
+    ref = F.conv2d(x_nchw, wt, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    _close(y, ref, 1e-2, 1e-2, 'conv_fprop with stats')
+
+
 @pytest.mark.parametrize('n,h,w,c,k,r,stride,pad', CONV_CASES)
 def test_conv_dgrad(n, h, w, c, k, r, stride, pad):
     ops, x_nchw, wt, x, wb, cs = _conv_case(n, h, w, c, k, r, stride, pad)
