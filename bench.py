@@ -197,14 +197,14 @@ def describe(name, a):
         x_b, y_b, w_b = cs.n * cs.h * cs.w * cs.c * 2, pix * cs.k * 2, cs.k * cs.c * cs.r * cs.s * 2
         nbytes = x_b + y_b + w_b if name != 'saicv_conv_wgrad' else x_b + y_b + cs.k * cs.c * cs.r * cs.s * 4
         return f'{name[6:]} {cs.r}x{cs.s}/{st} c{cs.c} k{cs.k} {cs.h}x{cs.w}', flops, float(nbytes)
-    if name == 'saicv_linear_fwd':
-        M, N, K = a[5], a[6], a[7]
+    if name == 'saicv_linear_fwd':      # (..., M, N, K, flags, out_f32, stream)
+        M, N, K = a[-6], a[-5], a[-4]
         return f'linear_fwd M{M} N{N} K{K}', 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)
-    if name == 'saicv_linear_dgrad':
-        M, N, K = a[4], a[5], a[6]
+    if name == 'saicv_linear_dgrad':    # (..., M, N, K, flags, out_f32, stream)
+        M, N, K = a[-6], a[-5], a[-4]
         return f'linear_dgrad M{M} N{N} K{K}', 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)
-    if name == 'saicv_linear_wgrad':
-        M, N, K = a[3], a[4], a[5]
+    if name == 'saicv_linear_wgrad':    # (dy, x, dw, M, N, K, splits, stream)
+        M, N, K = a[-5], a[-4], a[-3]
         return f'linear_wgrad M{M} N{N} K{K}', 2.0 * M * N * K, 2.0 * (M * K + M * N) + 4.0 * N * K
     return name[6:], 0.0, 0.0
 

@@ -468,9 +468,12 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     stage_rows(sY, dob, os, 0, Lq, L);
     for (int r = threadIdx.x; r < Lp; r += blockDim.x) sLse[r] = r < L ? lse[(long long)bh * L + r] : 0.f;
     // D[i] for every query: 4 lanes per row
+    // (every lane of a warp runs the quad shuffles of row_dot64: rows >= L are clamped, not skipped;
+    //  blockDim.x/4 divides Lp, so the trip count is warp-uniform)
     for (int r = (threadIdx.x >> 2); r < Lp; r += (blockDim.x >> 2)) {
-      const float dsum = r < L ? row_dot64(ob + (long long)r * os, dob + (long long)r * os, t) : 0.f;
-      if (t == 0) sD[r] = dsum;
+      const int rc = min(r, L - 1);
+      const float dsum = row_dot64(ob + (long long)rc * os, dob + (long long)rc * os, t);
+      if (t == 0) sD[r] = r < L ? dsum : 0.f;
     }
   }
   __syncthreads();
@@ -487,8 +490,9 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     load_a_frags_global(da, dob, os, tile0, L, g, t);
     const int r0 = tile0 + g, r1 = r0 + 8;
     const float ls0 = r0 < L ? lse[(long long)bh * L + r0] : 0.f, ls1 = r1 < L ? lse[(long long)bh * L + r1] : 0.f;
-    const float d0 = r0 < L ? row_dot64(ob + (long long)r0 * os, dob + (long long)r0 * os, t) : 0.f;
-    const float d1 = r1 < L ? row_dot64(ob + (long long)r1 * os, dob + (long long)r1 * os, t) : 0.f;
+    const int r0c = min(r0, L - 1), r1c = min(r1, L - 1);  // clamp (not skip): warp-wide shuffles inside
+    const float d0 = row_dot64(ob + (long long)r0c * os, dob + (long long)r0c * os, t);
+    const float d1 = row_dot64(ob + (long long)r1c * os, dob + (long long)r1c * os, t);
     // 32 keys per step: 8 independent accumulation chains keep the tensor pipe busier
     for (int k0 = 0; k0 < Lq; k0 += 32) {
       float s[4][4], dp[4][4];

@@ -39,14 +39,15 @@ def test_darknet53_step_matches_oracle():
     from simpleaicv_pytorch_training_examples_b200.classification import losses
     darknet, sd, model, x, y = _setup((8, 3, 128, 128))
     sd32 = {k: v.clone() for k, v in sd.items()}
-    l32, _, g32 = darknet.loss_and_grads(sd32, x, y)
+    l32, ls32, g32 = darknet.loss_and_grads(sd32, x, y)
     le, lse, ge = darknet.loss_and_grads(sd, x, y, emulate_bf16=True)
     logits = model(x.cuda())
     loss = losses.CELoss()(logits, y.cuda())
     loss.backward()
     torch.cuda.synchronize()
-    assert _rel_l2(logits.detach(), le) <= 5e-2, _rel_l2(logits.detach(), le)
-    assert abs(float(loss.detach()) - float(lse)) <= 1e-2 * abs(float(lse))
+    noise = _rel_l2(le, l32)
+    assert _rel_l2(logits.detach(), le) <= 2.5 * noise + 1e-2, (_rel_l2(logits.detach(), le), noise)
+    assert abs(float(loss.detach()) - float(lse)) <= 1e-2 * abs(float(lse)) + 2.5 * abs(float(lse) - float(ls32))
     grads = {n: p.grad.detach().float().cpu() for n, p in model.named_parameters()}
     cat = lambda d: torch.cat([d[n].flatten() for n in g32])
     mine_all, emu_all = _rel_l2(cat(grads), cat(g32)), _rel_l2(cat(ge), cat(g32))
