@@ -222,7 +222,8 @@ int saicv_linear_fwd(const void* x, const void* w, const float* bias, const floa
   if (row_scale && rows_per_scale <= 0) return set_error("saicv_linear_fwd: rows_per_scale must be > 0");
   p.row_scale = row_scale; p.rows_per_scale = rows_per_scale;
   if (stats_partial) {
-    if (bias || resid || out_f32) return set_error("saicv_linear_fwd: stats_partial needs a plain bf16 output (no bias / residual)");
+    if (bias || resid || out_f32 || (flags & EPI_DIRECT))
+      return set_error("saicv_linear_fwd: stats_partial needs a plain bf16 output through the TMA-store epilogue (no bias / residual)");
     p.epi_flags |= EPI_STATS; p.stats_partial = stats_partial;
   }
   p.out_f32 = out_f32; p.bias = bias; p.resid = resid; p.out = y; p.ldd = N; p.split_stride = 0;
@@ -295,7 +296,10 @@ int saicv_conv_fprop(const void* x, const void* w, float* stats_partial, void* y
   p.g.P = P; p.g.Q = Q; p.g.stride = cs->stride; p.g.lc_h = -cs->pad; p.g.lc_w = -cs->pad;
   p.g.R = cs->r; p.g.S = cs->s; p.g.cchunks = cs->c / 64; p.g.n_img = cs->n;
   p.epi_flags = flags & (EPI_RELU | EPI_DIRECT); p.out_f32 = 0; p.out = y; p.ldd = cs->k;
-  if (stats_partial) { p.epi_flags |= EPI_STATS; p.stats_partial = stats_partial; }
+  if (stats_partial) {
+    if (flags & EPI_DIRECT) return set_error("saicv_conv_fprop: stats_partial is not available with SAICV_EPI_DIRECT");
+    p.epi_flags |= EPI_STATS; p.stats_partial = stats_partial;
+  }
   return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream);
 }
 

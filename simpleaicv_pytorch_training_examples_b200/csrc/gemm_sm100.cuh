@@ -75,11 +75,27 @@ struct GemmParams {
   float* stats_partial;  // EPI_STATS: [gridDim.x][2][N] per-CTA column sums / sums of squares of the bf16 output
 };
 
+// Exact-erf GELU evaluated with the Abramowitz-Stegun 7.1.26 rational approximation of erf
+// (|error| < 1.5e-7, far below the bf16 resolution of the stored result) and one __expf:
+// exp(-z^2) with z = x/sqrt(2) is exp(-x^2/2), shared with the Gaussian density of gelu'.
+__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& pdf) {
+  const float e = __expf(-0.5f * x * x);
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, 1.0f + 0.3275911f * z);
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  const float erf_abs = 1.0f - poly * e;            // erf(|x|/sqrt2)
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));      // Phi(x)
+  pdf = 0.3989422804014327f * e;                    // phi(x)
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float cdf, pdf;
+  gelu_terms(x, cdf, pdf);
+  return x * cdf;
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  float cdf, pdf;
+  gelu_terms(x, cdf, pdf);
+  return cdf + x * pdf;
 }
 
 template <int BN>
@@ -370,33 +386,6 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         }
-        if (do_stats) {
-          // per-column sum / sum of squares of the values as they are stored (bf16-rounded): a
-          // 31-shuffle transpose-reduce leaves column col0+lane's total over this warp's 32 rows in
-          // lane `lane`; rows beyond M and columns beyond N hold exact zeros (TMA zero fill).
-          float sx[32], sq[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float r = __bfloat162float(__float2bfloat16_rn(f[j]));
-            sx[j] = r;
-            sq[j] = r * r;
-          }
-#pragma unroll
-          for (int o = 16, n = 16; o >= 1; o >>= 1, n >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              const float send_x = up ? sx[i] : sx[i + n], keep_x = up ? sx[i + n] : sx[i];
-              const float send_q = up ? sq[i] : sq[i + n], keep_q = up ? sq[i + n] : sq[i];
-              sx[i] = keep_x + __shfl_xor_sync(0xffffffffu, send_x, o);
-              sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, o);
-            }
-          }
-          if (col0 + lane < p.N) {
-            atomicAdd(&sStat[col0 + lane], sx[0]);
-            atomicAdd(&sStat[p.N + col0 + lane], sq[0]);
-          }
-        }
         if (direct) {
           if (row < p.M) {
             if (p.out_f32) {
@@ -463,6 +452,26 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     : "memory");
               }
               tma_store_commit();
+            }
+            if (do_stats) {
+              // BatchNorm statistics of the slice just staged (the bf16 values as stored): thread
+              // (col = gtid % 64, rows (gtid / 64) * 64 ..+63) walks one column of the swizzled
+              // buffer (conflict free: a warp reads 64 contiguous bytes of one row), concurrently
+              // with the TMA store that reads the same buffer.  Rows >= M / columns >= N are zero.
+              const int col = gtid & 63, r0s = (gtid >> 6) * 64;
+              float sx = 0.f, sq = 0.f;
+#pragma unroll 8
+              for (int r = r0s; r < r0s + 64; ++r) {
+                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
+                    sbuf + r * 128 + (((col >> 3) ^ (r & 7)) << 4) + (col & 7) * 2));
+                sx += v;
+                sq += v * v;
+              }
+              const int gcol = n0 + (c >> 1) * 64 + col;
+              if (gcol < p.N) {
+                atomicAdd(&sStat[gcol], sx);
+                atomicAdd(&sStat[p.N + gcol], sq);
+              }
             }
           }
         }
