@@ -454,23 +454,26 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_store_commit();
             }
             if (do_stats) {
-              // BatchNorm statistics of the slice just staged (the bf16 values as stored): thread
-              // (col = gtid % 64, rows (gtid / 64) * 64 ..+63) walks one column of the swizzled
-              // buffer (conflict free: a warp reads 64 contiguous bytes of one row), concurrently
-              // with the TMA store that reads the same buffer.  Rows >= M / columns >= N are zero.
-              const int col = gtid & 63, r0s = (gtid >> 6) * 64;
-              float sx = 0.f, sq = 0.f;
+              // BatchNorm statistics of the slice just staged (the bf16 values as stored), read back
+              // from the swizzled buffer (conflict free: a warp reads the 128 contiguous bytes of one
+              // row) concurrently with the TMA store of the same buffer.  Rows >= M / cols >= N are zero.
+              // thread (column pair gtid % 32, rows (gtid / 32) * 32 ..+31): one 32-bit load = 2 columns
+              const int cp2 = gtid & 31, r0s = (gtid >> 5) * 32;
+              float sx0 = 0.f, sq0 = 0.f, sx1 = 0.f, sq1 = 0.f;
 #pragma unroll 8
-              for (int r = r0s; r < r0s + 64; ++r) {
-                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
-                    sbuf + r * 128 + (((col >> 3) ^ (r & 7)) << 4) + (col & 7) * 2));
-                sx += v;
-                sq += v * v;
+              for (int r = r0s; r < r0s + 32; ++r) {
+                const uint32_t w2 = *reinterpret_cast<const uint32_t*>(
+                    sbuf + r * 128 + (((cp2 >> 2) ^ (r & 7)) << 4) + (cp2 & 3) * 4);
+                const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w2));
+                sx0 += v.x; sq0 += v.x * v.x;
+                sx1 += v.y; sq1 += v.y * v.y;
               }
-              const int gcol = n0 + (c >> 1) * 64 + col;
-              if (gcol < p.N) {
-                atomicAdd(&sStat[gcol], sx);
-                atomicAdd(&sStat[p.N + gcol], sq);
+              const int gcol = n0 + (c >> 1) * 64 + 2 * cp2;
+              if (gcol < p.N) {  // N is even: both columns of the pair are valid together
+                atomicAdd(&sStat[gcol], sx0);
+                atomicAdd(&sStat[gcol + 1], sx1);
+                atomicAdd(&sStat[p.N + gcol], sq0);
+                atomicAdd(&sStat[p.N + gcol + 1], sq1);
               }
             }
           }
