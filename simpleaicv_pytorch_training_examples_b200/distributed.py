@@ -108,6 +108,17 @@ class B200DataParallel(nn.Module):
         for b in self.buckets:
             b.ready.clear()
 
+    def reduce_now(self):
+        """All-reduce (average) the current contents of every bucket, e.g. after backward passes run
+        under no_sync().  Parameters without a gradient take part as zeros."""
+        old, self.require_sync = self.require_sync, True
+        try:
+            for b in self.buckets:
+                b.ready.update(id(p) for p, _ in b.params if p.grad is not None)
+            self._finish()
+        finally:
+            self.require_sync = old
+
     @contextlib.contextmanager
     def no_sync(self):
         """Gradient accumulation: skip the all-reduce for backward passes run inside."""

@@ -63,6 +63,14 @@ def _worker(rank, world, port, q):
         assert torch.allclose(net.b.bias.grad, torch.full_like(net.b.bias, float(rank + 1)))
         net.fake_backward(rank, scale=2.0)
         assert torch.allclose(net.b.bias.grad, torch.full_like(net.b.bias, 1.5 * 3.0))
+        # reduce_now(): explicit reduction of gradients produced under no_sync()
+        for p in net.parameters():
+            p.grad = None
+        with ddp.no_sync():
+            net.fake_backward(rank)
+        ddp.reduce_now()
+        assert torch.allclose(net.b.bias.grad, torch.full_like(net.b.bias, 1.5))
+        assert torch.allclose(net.a.weight.grad, torch.full_like(net.a.weight, 6.0))
         q.put((rank, 'ok'))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
