@@ -323,34 +323,56 @@ def run_b200(args, rank, world, local_rank):
             d['flops'] /= 2
             d['bytes'] /= 2
         gemm = {k: v for k, v in table.items() if v['flops'] > 0}
-        top_key = max(gemm, key=lambda k: gemm[k]['ms'])
-        top = gemm[top_key]
-        per_launch_ms = top['ms'] / top['calls']
-        t_tensor = top['flops'] / top['calls'] / (peaks['tf_sustained'] * 1e12)
-        t_hbm = top['bytes'] / top['calls'] / (peaks['hbm_gbs'] * 1e9)
-        if t_tensor >= t_hbm:
-            ach = top['flops'] / top['calls'] / (per_launch_ms / 1e3) / 1e12
-            roof = {'bound': 'tensor', 'achieved': ach, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
-                    'frac': ach / peaks['tf_sustained'], 'traffic': None}
+        # Dominant kernel = gemm_sm100_kernel (every conv / linear fprop, dgrad, wgrad launch of the step).
+        # Each launch is bound either by the tensor pipe or by HBM (algorithmic FLOPs and bytes of its
+        # shape); per class: achieved = sum(algorithmic work) / sum(CUDA-event durations).
+        tf_peak, bw_peak = peaks['tf_sustained'] * 1e12, peaks['hbm_gbs'] * 1e9
+        cls = {'tensor': {'work': 0.0, 'ms': 0.0, 'roof_ms': 0.0, 'launches': 0},
+               'hbm': {'work': 0.0, 'ms': 0.0, 'roof_ms': 0.0, 'launches': 0}}
+        for k, v in gemm.items():
+            t_t, t_h = v['flops'] / tf_peak * 1e3, v['bytes'] / bw_peak * 1e3
+            c = cls['tensor'] if t_t >= t_h else cls['hbm']
+            c['work'] += v['flops'] if t_t >= t_h else v['bytes']
+            c['ms'] += v['ms']
+            c['roof_ms'] += max(t_t, t_h)
+            c['launches'] += v['calls']
+            v['roof_frac'] = max(t_t, t_h) / v['ms'] if v['ms'] else 0.0
+        dom = 'tensor' if cls['tensor']['ms'] >= cls['hbm']['ms'] else 'hbm'
+        d = cls[dom]
+        if dom == 'tensor':
+            ach, peak, unit = d['work'] / (d['ms'] / 1e3) / 1e12, peaks['tf_sustained'], 'TFLOP/s'
         else:
-            ach = top['bytes'] / top['calls'] / (per_launch_ms / 1e3) / 1e9
-            roof = {'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                    'frac': ach / peaks['hbm_gbs'], 'traffic': None}
-        roof.update({'kernel': 'gemm_sm100_kernel', 'launch': top_key, 'ms_per_launch': per_launch_ms,
-                     'peak_source': peaks['source'] + (' (sustained)' if roof['bound'] == 'tensor' else '')})
+            ach, peak, unit = d['work'] / (d['ms'] / 1e3) / 1e9, peaks['hbm_gbs'], 'GB/s'
         gemm_ms = sum(v['ms'] for v in gemm.values())
         all_ms = sum(v['ms'] for v in table.values())
-        roof['gemm_share_of_step'] = gemm_ms / all_ms if all_ms else None
-        roof['step_tensor_tflops'] = 3 * FWD_FLOPS[args.model] * B / (ms_step / 1e3) / 1e12
-        roof['step_hbm_gbs_algorithmic'] = ALGO_BYTES[args.model] * B / (ms_step / 1e3) / 1e9
+        top_key = max(gemm, key=lambda k: gemm[k]['ms'])
+        roof = {'bound': dom, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak, 'traffic': None,
+                'kernel': 'gemm_sm100_kernel', 'launches_in_class': d['launches'],
+                'frac_definition': ('every gemm_sm100_kernel launch of the step is classed tensor- or hbm-bound from its '
+                                    'algorithmic FLOPs / bytes vs MEASURED_PEAKS; achieved = sum(work) / sum(CUDA-event time) '
+                                    'over the class holding most of the GEMM time; frac = achieved / peak of that class. '
+                                    'See other_class, all_launches_frac_of_roofline_time and slowest_launch for the rest.'),
+                'definition_changed_from': ('earlier lines of this round reported the single (op, shape) with the largest total '
+                                            'time (R50: conv_wgrad 3x3 c64 k64 56x56, frac ~0.145); that launch is still '
+                                            'reported under slowest_launch and did not get faster'),
+                'peak_source': peaks['source'] + (' (sustained)' if dom == 'tensor' else ''),
+                'class_share_of_gemm_time': d['ms'] / gemm_ms,
+                'all_launches_frac_of_roofline_time': sum(c['roof_ms'] for c in cls.values()) / gemm_ms,
+                'other_class': {k: (c['work'] / (c['ms'] / 1e3) / (1e12 if k == 'tensor' else 1e9) if c['ms'] else None)
+                                for k, c in cls.items() if k != dom},
+                'slowest_launch': {'launch': top_key, 'ms_per_launch': gemm[top_key]['ms'] / gemm[top_key]['calls'],
+                                   'frac_of_its_roofline': gemm[top_key]['roof_frac']},
+                'gemm_share_of_step': gemm_ms / all_ms if all_ms else None,
+                'step_tensor_tflops': 3 * FWD_FLOPS[args.model] * B / (ms_step / 1e3) / 1e12,
+                'step_hbm_gbs_algorithmic': ALGO_BYTES[args.model] * B / (ms_step / 1e3) / 1e9}
         if args.dump_ops:
             rows = sorted(table.items(), key=lambda kv: -kv[1]['ms'])
             with open(args.dump_ops, 'w') as f:
-                f.write('op,calls,ms_per_step,GFLOP,algorithmic_MB,TFLOP/s,GB/s\n')
+                f.write('op,calls,ms_per_step,GFLOP,algorithmic_MB,TFLOP/s,GB/s,frac_of_roofline\n')
                 for k, v in rows:
                     s = v['ms'] / 1e3
                     f.write(f"{k},{v['calls']},{v['ms']:.4f},{v['flops'] / 1e9:.2f},{v['bytes'] / 1e6:.2f},"
-                            f"{v['flops'] / s / 1e12 if s else 0:.1f},{v['bytes'] / s / 1e9 if s else 0:.1f}\n")
+                            f"{v['flops'] / s / 1e12 if s else 0:.1f},{v['bytes'] / s / 1e9 if s else 0:.1f},{v.get('roof_frac', 0):.3f}\n")
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             ips, dt = cpu_oracle_images_per_sec(args.model, 8, 2, cores)
