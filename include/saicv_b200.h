@@ -145,6 +145,13 @@ int saicv_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, int n, int h
                            void* stream);
 int saicv_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int n, int h, int w,
                            int c, void* stream);
+/* General nn.MaxPool2d(k, stride) on NHWC bf16 (darknet.py:105,161-213: 2x2/2 pools; :212-213
+ * ZeroPad2d((0,1,0,1)) + MaxPool2d(2,1) = pad 0, pad_hi 1, oob_zero 1: padded taps count as 0 and
+ * get no gradient).  Output extent (h + pad + pad_hi - k) / stride + 1; argmax byte = r*k + s. */
+int saicv_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int n, int h, int w, int c, int k,
+                      int stride, int pad, int pad_hi, int oob_zero, void* stream);
+int saicv_maxpool_bwd(const void* dy, const uint8_t* argmax, void* dx, int n, int h, int w, int c,
+                      int k, int stride, int pad, int pad_hi, void* stream);
 int saicv_avgpool_fwd(const void* x, void* y, int n, int hw, int c, void* stream);
 int saicv_avgpool_bwd(const void* dy, void* dx, int n, int hw, int c, void* stream);
 /* column sums of a bf16 (or fp32 when is_f32) [rows][c] matrix into fp32 out[c] ((+)= when
@@ -163,8 +170,8 @@ int saicv_layernorm_fwd(const float* x, const float* gamma, const float* beta, v
  * dgamma/dbeta (+)= column reductions (zeroed first unless accumulate). */
 int saicv_layernorm_bwd(const void* dy, const float* x, const float* gamma, const float* stats,
                         const float* dres, float* dx, void* dx_bf16, const float* bf16_row_scale,
-                        int rows_per_scale, float* dgamma, float* dbeta, long long rows, int c,
-                        int accumulate, void* stream);
+                        int rows_per_scale, float* partials /* [SAICV_BN_PARTIAL_ROWS][2*c] workspace */,
+                        float* dgamma, float* dbeta, long long rows, int c, int accumulate, void* stream);
 /* nn.GELU() exact erf (vit.py:87-89): h = gelu(u); du = dh * gelu'(u); bf16, n % 8 == 0. */
 int saicv_gelu_fwd(const void* u, void* h, long long n, void* stream);
 int saicv_gelu_bwd(const void* dh, const void* u, void* du, long long n, void* stream);

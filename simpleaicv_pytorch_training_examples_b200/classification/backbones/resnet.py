@@ -92,7 +92,8 @@ class _ResNetBase(nn.Module):
     def _runtime(self):
         rt = self.__dict__.get('_rt')
         if rt is None:
-            rt = ResNetRT(self, has_maxpool=hasattr(self, 'maxpool1'))
+            rt = ResNetRT(self, has_maxpool=hasattr(self, 'maxpool1'),
+                          checkpoint=getattr(self, 'use_gradient_checkpoint', False))
             self.__dict__['_rt'] = rt  # not a submodule / not in state_dict
         return rt
 
@@ -104,8 +105,6 @@ class _ResNetBase(nn.Module):
         if not x.is_cuda:
             raise RuntimeError('this model runs on B200 kernels only; move the batch to the GPU '
                                '(no CPU fallback exists)')
-        if getattr(self, 'use_gradient_checkpoint', False):
-            raise NotImplementedError('use_gradient_checkpoint is not implemented by the B200 runtime yet')
         return run_network(self._runtime(), x.float(), self.training)
 
 

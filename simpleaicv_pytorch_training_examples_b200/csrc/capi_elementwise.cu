@@ -61,11 +61,19 @@ __device__ __forceinline__ V8 ldg8(const void* p, long long vec_idx) {
 __device__ __forceinline__ void stg8(void* p, long long vec_idx, const V8& v) {
   *(reinterpret_cast<V8*>(p) + vec_idx) = v;
 }
+// act: 0 none, 1 ReLU, 2 LeakyReLU(0.1), 3 SiLU (darknet.py:16-31 ActivationBlock)
 __device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == 3) return v * __fdividef(1.f, 1.f + __expf(-v));
   return act == 1 ? fmaxf(v, 0.f) : (act == 2 ? (v > 0.f ? v : 0.1f * v) : v);
 }
 __device__ __forceinline__ float act_grad(float out, int act) {
-  // derivative expressed through the activated output (sign is preserved by ReLU / LeakyReLU)
+  // ReLU / LeakyReLU: derivative expressed through the activated output OR the pre-activation (same
+  // sign).  SiLU: `out` must be the pre-activation z (mask-recompute path only, enforced by the C ABI):
+  // silu'(z) = s(z) * (1 + z * (1 - s(z))).
+  if (act == 3) {
+    const float sg = __fdividef(1.f, 1.f + __expf(-out));
+    return sg * (1.f + out * (1.f - sg));
+  }
   return act == 1 ? (out > 0.f ? 1.f : 0.f) : (act == 2 ? (out > 0.f ? 1.f : 0.1f) : 1.f);
 }
 
@@ -626,8 +634,12 @@ __global__ void add_strided2_kernel(void* __restrict__ dx, const void* __restric
 }
 
 // ----------------------------------------------------------------------------- pooling
+// General K x K / stride max-pool over NHWC bf16.  Window of output (p, q) starts at
+// (p*stride - pad, q*stride - pad).  Out-of-range taps are skipped (-inf padding, nn.MaxPool2d) or,
+// with oob_zero, take part with the value 0 (nn.ZeroPad2d followed by an unpadded pool,
+// darknet.py:212-213): their code is 255 and they receive no gradient.  argmax byte = r*K + s.
 __global__ void maxpool_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, uint8_t* __restrict__ amax,
-                                   int N, int H, int W, int C, int P, int Q) {
+                                   int N, int H, int W, int C, int P, int Q, int K, int stride, int pad, int oob_zero) {
   const int vpr = C >> 3;
   const long long total = (long long)N * P * Q * vpr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -642,19 +654,23 @@ __global__ void maxpool_fwd_kernel(const void* __restrict__ x, void* __restrict_
 #pragma unroll
     for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; arg[k] = 0; }
     bool first = true;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int h = 2 * p - 1 + r;
-      if (h < 0 || h >= H) continue;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int w = 2 * q - 1 + s;
-        if (w < 0 || w >= W) continue;
+    for (int r = 0; r < K; ++r) {
+      const int h = stride * p - pad + r;
+      for (int s = 0; s < K; ++s) {
+        const int w = stride * q - pad + s;
+        const bool inside = h >= 0 && h < H && w >= 0 && w < W;
+        if (!inside && !oob_zero) continue;
         float f[8];
-        unpack8(ldg8(x, ((n * H + h) * W + w) * vpr + v), f);
+        if (inside) {
+          unpack8(ldg8(x, ((n * H + h) * W + w) * vpr + v), f);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = 0.f;
+        }
+        const int code = inside ? r * K + s : 255;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (first || f[k] > best[k]) { best[k] = f[k]; arg[k] = r * 3 + s; }
+          if (first || f[k] > best[k]) { best[k] = f[k]; arg[k] = code; }
         first = false;
       }
     }
@@ -667,7 +683,8 @@ __global__ void maxpool_fwd_kernel(const void* __restrict__ x, void* __restrict_
 }
 
 __global__ void maxpool_bwd_kernel(const void* __restrict__ dy, const uint8_t* __restrict__ amax,
-                                   void* __restrict__ dx, int N, int H, int W, int C, int P, int Q) {
+                                   void* __restrict__ dx, int N, int H, int W, int C, int P, int Q, int K, int stride,
+                                   int pad) {
   const int vpr = C >> 3;
   const long long total = (long long)N * H * W * vpr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -680,22 +697,23 @@ __global__ void maxpool_bwd_kernel(const void* __restrict__ dy, const uint8_t* _
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    // output windows (p, q) that contain (h, w): 2p-1 <= h <= 2p+1
-    const int p_lo = h >> 1, p_hi = (h + 1) >> 1;
-    const int q_lo = w >> 1, q_hi = (w + 1) >> 1;
+    // output windows (p, q) that contain (h, w): stride*p - pad <= h <= stride*p - pad + K - 1
+    const int hp = h + pad, wp = w + pad;
+    const int p_hi = min(hp / stride, P - 1), q_hi = min(wp / stride, Q - 1);
+    const int p_lo = max((hp - K + stride) / stride, 0), q_lo = max((wp - K + stride) / stride, 0);
     for (int p = p_lo; p <= p_hi; ++p) {
-      if (p >= P) continue;
-      const int r = h - (2 * p - 1);
+      const int r = hp - stride * p;
+      if (r < 0 || r >= K) continue;
       for (int q = q_lo; q <= q_hi; ++q) {
-        if (q >= Q) continue;
-        const int s = w - (2 * q - 1);
+        const int s = wp - stride * q;
+        if (s < 0 || s >= K) continue;
         const long long oi = ((n * P + p) * Q + q) * vpr + v;
         const uint64_t packed = reinterpret_cast<const uint64_t*>(amax)[oi];
         float g[8];
         unpack8(ldg8(dy, oi), g);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if ((int)((packed >> (8 * k)) & 0xff) == r * 3 + s) acc[k] += g[k];
+          if ((int)((packed >> (8 * k)) & 0xff) == r * K + s) acc[k] += g[k];
       }
     }
     stg8(dx, i, pack8(acc));
@@ -787,6 +805,7 @@ int saicv_bn_bwd_reduce(const void* dout, const void* out, const void* y, const 
                         void* stream) {
   if (act != 0 && out == nullptr && scale_shift == nullptr)
     return set_error("saicv_bn_bwd_reduce: need the activated output or scale_shift to form the activation mask");
+  if ((act & 7) == 3 && out != nullptr) return set_error("saicv_bn_bwd_reduce: SiLU needs the recompute path (out == NULL, scale_shift given)");
   int nblk;
   if (int e = launch_colreduce<1>(dout, out, y, saved, scale_shift, partials, rows, c, act, &nblk, ST)) return e;
   return fold(partials, sums, nblk, 2 * c, 0, ST);
@@ -797,6 +816,7 @@ int saicv_bn_bwd_apply(const void* dout, const void* out, const void* y, const f
                        long long rows, int c, int act, int accumulate, void* stream) {
   if (act != 0 && out == nullptr && scale_shift == nullptr)
     return set_error("saicv_bn_bwd_apply: need the activated output or scale_shift to form the activation mask");
+  if ((act & 7) == 3 && out != nullptr) return set_error("saicv_bn_bwd_apply: SiLU needs the recompute path (out == NULL, scale_shift given)");
   SlabGeom g;
   int blocks;
   if (!slab_geom(rows, c, UNROLL, &g, &blocks)) return 1;
@@ -882,19 +902,32 @@ int saicv_add_strided2(void* dx, const void* dd, int n, int p, int q, int h, int
   return check_launch("add_strided2_kernel");
 }
 
-int saicv_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, int n, int h, int w, int c, void* stream) {
-  if (c % 8) return set_error("saicv_maxpool3x3s2_fwd: C %% 8 != 0");
-  const int P = (h + 2 - 3) / 2 + 1, Q = (w + 2 - 3) / 2 + 1;
-  maxpool_fwd_kernel<<<grid_for((long long)n * P * Q * (c / 8)), kThreads, 0, ST>>>(x, y, argmax, n, h, w, c, P, Q);
+int saicv_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int n, int h, int w, int c, int k, int stride, int pad,
+                      int pad_hi, int oob_zero, void* stream) {
+  if (c % 8) return set_error("saicv_maxpool_fwd: C %% 8 != 0");
+  if (k < 1 || k > 15 || stride < 1) return set_error("saicv_maxpool_fwd: unsupported window %d / stride %d", k, stride);
+  const int P = (h + pad + pad_hi - k) / stride + 1, Q = (w + pad + pad_hi - k) / stride + 1;
+  maxpool_fwd_kernel<<<grid_for((long long)n * P * Q * (c / 8)), kThreads, 0, ST>>>(x, y, argmax, n, h, w, c, P, Q, k, stride,
+                                                                                    pad, oob_zero);
   return check_launch("maxpool_fwd_kernel");
+}
+
+int saicv_maxpool_bwd(const void* dy, const uint8_t* argmax, void* dx, int n, int h, int w, int c, int k, int stride,
+                      int pad, int pad_hi, void* stream) {
+  if (c % 8) return set_error("saicv_maxpool_bwd: C %% 8 != 0");
+  const int P = (h + pad + pad_hi - k) / stride + 1, Q = (w + pad + pad_hi - k) / stride + 1;
+  maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8)), kThreads, 0, ST>>>(dy, argmax, dx, n, h, w, c, P, Q, k, stride,
+                                                                                    pad);
+  return check_launch("maxpool_bwd_kernel");
+}
+
+int saicv_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* argmax, int n, int h, int w, int c, void* stream) {
+  return saicv_maxpool_fwd(x, y, argmax, n, h, w, c, 3, 2, 1, 1, 0, stream);
 }
 
 int saicv_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int n, int h, int w, int c,
                            void* stream) {
-  if (c % 8) return set_error("saicv_maxpool3x3s2_bwd: C %% 8 != 0");
-  const int P = (h + 2 - 3) / 2 + 1, Q = (w + 2 - 3) / 2 + 1;
-  maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8)), kThreads, 0, ST>>>(dy, argmax, dx, n, h, w, c, P, Q);
-  return check_launch("maxpool_bwd_kernel");
+  return saicv_maxpool_bwd(dy, argmax, dx, n, h, w, c, 3, 2, 1, 1, stream);
 }
 
 int saicv_avgpool_fwd(const void* x, void* y, int n, int hw, int c, void* stream) {

@@ -74,13 +74,15 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 }
 
 // dx = dres + rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)), dxhat = dy*gamma; dgamma/dbeta
-// accumulated per warp in registers, folded through shared memory, one atomicAdd per block/col.
+// accumulated per warp in registers, folded through shared memory in a fixed order into one
+// partial row per block ([gridDim.x][2][C]); ln_fold_kernel sums the rows, again in a fixed order,
+// so the parameter gradients are bit-reproducible (no atomics).
 template <int NCH>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ stats, const float* __restrict__ dres, float* __restrict__ dx,
               __nv_bfloat16* __restrict__ dx_bf16, const float* __restrict__ row_scale, int rows_per_scale,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, long long M) {
+              float* __restrict__ partials, long long M) {
   constexpr int C = NCH * 128;
   __shared__ float red[8][C];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -135,9 +137,20 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
       float s = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) s += red[w][c];
-      atomicAdd((pass == 0 ? dgamma : dbeta) + c, s);
+      partials[((long long)blockIdx.x * 2 + pass) * C + c] = s;
     }
   }
+}
+
+// dgamma / dbeta (+)= sum over the per-block partial rows, fixed order
+__global__ void ln_fold_kernel(const float* __restrict__ partials, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                               int nblk, int C, int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2C-1
+  if (j >= 2 * C) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partials[(long long)b * 2 * C + j];
+  float* dst = j < C ? dgamma + j : dbeta + (j - C);
+  *dst = accumulate ? *dst + s : s;
 }
 
 // ----------------------------------------------------------------------------- GELU (exact, erf)
@@ -598,25 +611,24 @@ int saicv_layernorm_fwd(const float* x, const float* gamma, const float* beta, v
 }
 
 int saicv_layernorm_bwd(const void* dy, const float* x, const float* gamma, const float* stats, const float* dres,
-                        float* dx, void* dx_bf16, const float* bf16_row_scale, int rows_per_scale, float* dgamma,
-                        float* dbeta, long long rows, int c, int accumulate, void* stream) {
+                        float* dx, void* dx_bf16, const float* bf16_row_scale, int rows_per_scale, float* partials,
+                        float* dgamma, float* dbeta, long long rows, int c, int accumulate, void* stream) {
   if (bf16_row_scale && rows_per_scale <= 0) return set_error("saicv_layernorm_bwd: rows_per_scale must be > 0");
-  if (!accumulate) {
-    cudaMemsetAsync(dgamma, 0, sizeof(float) * c, ST);
-    cudaMemsetAsync(dbeta, 0, sizeof(float) * c, ST);
-  }
+  if (!partials) return set_error("saicv_layernorm_bwd: needs a [SAICV_BN_PARTIAL_ROWS][2*c] fp32 workspace");
   const int grid = grid_1d(rows, 8 * 8, 148 * 2);
   const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(dy);
   __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   switch (c) {
-    case 768: ln_bwd_kernel<6><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, dgamma, dbeta, rows); break;
-    case 1024: ln_bwd_kernel<8><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, dgamma, dbeta, rows); break;
-    case 1280: ln_bwd_kernel<10><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, dgamma, dbeta, rows); break;
-    case 256: ln_bwd_kernel<2><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, dgamma, dbeta, rows); break;
-    case 128: ln_bwd_kernel<1><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, dgamma, dbeta, rows); break;
+    case 768: ln_bwd_kernel<6><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
+    case 1024: ln_bwd_kernel<8><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
+    case 1280: ln_bwd_kernel<10><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
+    case 256: ln_bwd_kernel<2><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
+    case 128: ln_bwd_kernel<1><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
     default: return set_error("saicv_layernorm_bwd: unsupported width %d", c);
   }
-  return check_launch("ln_bwd_kernel");
+  if (int e = check_launch("ln_bwd_kernel")) return e;
+  ln_fold_kernel<<<(2 * c + 127) / 128, 128, 0, ST>>>(partials, dgamma, dbeta, grid, c, accumulate);
+  return check_launch("ln_fold_kernel");
 }
 
 int saicv_gelu_fwd(const void* u, void* h, long long n, void* stream) {

@@ -457,23 +457,41 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               // BatchNorm statistics of the slice just staged (the bf16 values as stored), read back
               // from the swizzled buffer (conflict free: a warp reads the 128 contiguous bytes of one
               // row) concurrently with the TMA store of the same buffer.  Rows >= M / cols >= N are zero.
-              // thread (column pair gtid % 32, rows (gtid / 32) * 32 ..+31): one 32-bit load = 2 columns
-              const int cp2 = gtid & 31, r0s = (gtid >> 5) * 32;
-              float sx0 = 0.f, sq0 = 0.f, sx1 = 0.f, sq1 = 0.f;
-#pragma unroll 8
-              for (int r = r0s; r < r0s + 32; ++r) {
-                const uint32_t w2 = *reinterpret_cast<const uint32_t*>(
-                    sbuf + r * 128 + (((cp2 >> 2) ^ (r & 7)) << 4) + (cp2 & 3) * 4);
-                const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w2));
-                sx0 += v.x; sq0 += v.x * v.x;
-                sx1 += v.y; sq1 += v.y * v.y;
+              // Fixed summation order (bit-reproducible, no atomics): warp wq of the half owns columns
+              // wq*16..+15 of the slice for all 128 rows.  Lane l reads 8 bytes (4 columns) of row
+              // i*8 + l/4: the 8 rows of one load hit 8 distinct swizzled 16-byte chunks, so the
+              // 256-byte request is conflict free.  The 8 row-lanes are then folded by shuffles and
+              // lanes 0..3 add to the accumulators they alone own.
+              const int wq = gtid >> 5;
+              const int piece = lane & 3;
+              const int chunk = wq * 2 + (piece >> 1);
+              float sx[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+              for (int i = 0; i < 16; ++i) {
+                const int r = i * 8 + (lane >> 2);
+                const uint2 w2 = *reinterpret_cast<const uint2*>(sbuf + r * 128 + ((chunk ^ (r & 7)) << 4) + (piece & 1) * 8);
+                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w2.x));
+                const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w2.y));
+                sx[0] += a.x; sq[0] += a.x * a.x;
+                sx[1] += a.y; sq[1] += a.y * a.y;
+                sx[2] += b.x; sq[2] += b.x * b.x;
+                sx[3] += b.y; sq[3] += b.y * b.y;
               }
-              const int gcol = n0 + (c >> 1) * 64 + 2 * cp2;
-              if (gcol < p.N) {  // N is even: both columns of the pair are valid together
-                atomicAdd(&sStat[gcol], sx0);
-                atomicAdd(&sStat[gcol + 1], sx1);
-                atomicAdd(&sStat[p.N + gcol], sq0);
-                atomicAdd(&sStat[p.N + gcol + 1], sq1);
+#pragma unroll
+              for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  sx[j] += __shfl_xor_sync(0xffffffffu, sx[j], o);
+                  sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], o);
+                }
+              }
+              const int gcol = n0 + (c >> 1) * 64 + wq * 16 + piece * 4;
+              if (lane < 4 && gcol < p.N) {  // N % 8 == 0: the 4 columns are valid together
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  sStat[gcol + j] += sx[j];
+                  sStat[p.N + gcol + j] += sq[j];
+                }
               }
             }
           }

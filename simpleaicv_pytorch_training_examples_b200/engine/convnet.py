@@ -19,7 +19,7 @@ import torch
 
 from .. import ops
 
-ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SILU = 0, 1, 2, 3
 # BatchNorm batch statistics are accumulated by the conv GEMM's epilogue instead of a separate pass over y
 FUSE_BN_STATS = True
 
@@ -85,8 +85,6 @@ class ConvBN:
         self.kpad = _round_up(r * s * c, 64) if self.is_stem else r * s * self.cp
         self.w_bf16 = None
         self.w_version = None
-        self.ss = None
-        self.saved = None
         self.sums = None
 
     # ---- parameters
@@ -96,9 +94,7 @@ class ConvBN:
         if self.w_bf16 is None or self.w_bf16.device != w.device:
             dev = w.device
             self.w_bf16 = torch.empty(self.kp, self.kpad, device=dev, dtype=torch.bfloat16)
-            self.ss = torch.zeros(2, self.kp, device=dev)
-            self.saved = torch.empty(2, self.kp, device=dev)
-            self.sums = torch.zeros(2, self.kp, device=dev)
+            self.sums = torch.zeros(2, self.kp, device=dev)   # backward scratch (consumed within one bn_bwd)
             if self.padded:
                 self.gamma_p = torch.ones(self.kp, device=dev)
                 self.beta_p = torch.zeros(self.kp, device=dev)
@@ -152,11 +148,16 @@ class ConvBN:
         tape['y'] = y
         return y
 
-    def bn_prepare(self, y, training, tape=None):
-        """Fills self.ss (scale/shift) from batch statistics (training) or running stats (eval)."""
+    def bn_prepare(self, y, training, tape):
+        """Computes this forward's BN coefficients into the tape: tape['ss'] = (scale, shift) and
+        tape['saved'] = (mean, rstd), from batch statistics (training) or running stats (eval).  They
+        live in the tape (not on the unit) so that a second forward of the same module before the
+        backward of the first (eval pass, micro-batches, EMA/teacher pass) cannot clobber them."""
         bn = self.bn
         rows = y.numel() // self.kp
         track = bn.track_running_stats
+        ss = tape['ss'] = torch.empty(2, self.kp, device=y.device)
+        saved = tape['saved'] = torch.empty(2, self.kp, device=y.device)
         if training or not track:
             momentum = bn.momentum if bn.momentum is not None else 0.1
             fused = tape.get('stats') if tape is not None else None
@@ -169,7 +170,7 @@ class ConvBN:
                 self.rv_p[:self.k].copy_(bn.running_var)
             rm = (self.rm_p if self.padded else bn.running_mean) if track else None
             rv = (self.rv_p if self.padded else bn.running_var) if track else None
-            ops.bn_finalize(partials, self._gamma(), self._beta(), rm, rv, self.ss, self.saved, rows, bn.eps, momentum,
+            ops.bn_finalize(partials, self._gamma(), self._beta(), rm, rv, ss, saved, rows, bn.eps, momentum,
                             partial_rows=prow)
             if self.padded and track:
                 bn.running_mean.copy_(self.rm_p[:self.k])
@@ -178,19 +179,18 @@ class ConvBN:
                 bn.num_batches_tracked.add_(1)
         else:
             scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
-            self.ss.zero_()
-            self.ss[0, :self.k].copy_(scale)
-            self.ss[1, :self.k].copy_(bn.bias.detach() - bn.running_mean * scale)
+            ss.zero_()
+            ss[0, :self.k].copy_(scale)
+            ss[1, :self.k].copy_(bn.bias.detach() - bn.running_mean * scale)
 
-    def forward(self, a_in, tape, training, res=None, res_unit=None):
-        """conv -> BN -> (+res) -> act (or act then +res when res_after_act).  res_unit: ConvBN whose
-        BN is applied to `res` on the fly (downsample branch)."""
+    def forward(self, a_in, tape, training, res=None, res_ss=None):
+        """conv -> BN -> (+res) -> act (or act then +res when res_after_act).  res_ss: BN scale/shift
+        applied to `res` on the fly (downsample branch)."""
         y = self.conv_fwd(a_in, tape, want_stats=training and FUSE_BN_STATS)
         self.bn_prepare(y, training, tape)
         out = torch.empty_like(y)
         act = self.act | (8 if (self.res_after_act and res is not None) else 0)
-        ops.bn_apply(y, self.ss, out, act, res=res,
-                     res_scale_shift=res_unit.ss if res_unit is not None else None)
+        ops.bn_apply(y, tape['ss'], out, act, res=res, res_scale_shift=res_ss)
         tape['out'] = out
         return out
 
@@ -204,15 +204,16 @@ class ConvBN:
         act = self.act if act is None else act
         y = tape['y']
         mask_src = act_out if act != ACT_NONE else None
-        ss = self.ss if (act != ACT_NONE and mask_src is None) else None
-        ops.bn_bwd_reduce(dout, mask_src, y, self.saved, self.sums, act, scale_shift=ss)
+        ss = tape['ss'] if (act != ACT_NONE and mask_src is None) else None
+        saved = tape['saved']
+        ops.bn_bwd_reduce(dout, mask_src, y, saved, self.sums, act, scale_shift=ss)
         dy = torch.empty_like(y)
         dres = torch.empty_like(y) if want_dres else None
         gbuf, gacc = sink.begin(self.bn.weight)
         bbuf, bacc = sink.begin(self.bn.bias)
         assert gacc == bacc
         if self.padded:
-            ops.bn_bwd_apply(dout, mask_src, y, self.saved, self.gamma_p, self.sums, dy, dres, self.dg_p, self.db_p,
+            ops.bn_bwd_apply(dout, mask_src, y, saved, self.gamma_p, self.sums, dy, dres, self.dg_p, self.db_p,
                              act, accumulate=False, scale_shift=ss)
             if gacc:
                 gbuf.add_(self.dg_p[:self.k])
@@ -221,7 +222,7 @@ class ConvBN:
                 gbuf.copy_(self.dg_p[:self.k])
                 bbuf.copy_(self.db_p[:self.k])
         else:
-            ops.bn_bwd_apply(dout, mask_src, y, self.saved, self.bn.weight.detach(), self.sums, dy, dres,
+            ops.bn_bwd_apply(dout, mask_src, y, saved, self.bn.weight.detach(), self.sums, dy, dres,
                              gbuf, bbuf, act, accumulate=gacc, scale_shift=ss)
         sink.done(self.bn.weight, gbuf)
         sink.done(self.bn.bias, bbuf)
@@ -282,7 +283,7 @@ class ResidualBlockRT:
             td = tape.setdefault('d', dict())
             yd = self.down.conv_fwd(a_in, td, want_stats=training and FUSE_BN_STATS)
             self.down.bn_prepare(yd, training, td)
-            out = last.forward(x, tl, training, res=yd, res_unit=self.down)
+            out = last.forward(x, tl, training, res=yd, res_ss=td['ss'])
         else:
             out = last.forward(x, tl, training, res=a_in)
         return out
@@ -354,85 +355,63 @@ class DarkBlockRT:
         return ops.add_bf16(dx, dout)
 
 
-class ResNetRT:
-    """Whole-network runtime for the conv -> BN -> act classifiers: ResNet (resnet.py:158-245),
-    ResNetCifar (resnetforcifar.py:27-108) and Darknet53 (darknet.py:323-432): stem [+ maxpool] +
-    a sequence of stages + global average pool + fc."""
+class MaxPoolRT:
+    """nn.MaxPool2d stage (DarkNet-19 / tiny 2x2 pools, darknet.py:105,161-213)."""
 
-    def __init__(self, model, has_maxpool, stem=None, blocks=None):
-        self.model = model
-        self.has_maxpool = has_maxpool
-        if stem is None:
-            stem = ConvBN(model.conv1, ACT_RELU)
-            blocks = []
-            for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
-                for blk in layer:
-                    blocks.append(ResidualBlockRT(blk))
-        self.stem = stem
-        self.blocks = blocks
-        self.fc = model.fc
-        self.fc_w_bf16 = None
-        self.fc_b_pad = None
-        self.fc_version = None
-        self.sink = GradSink()
-        self.tape = None
+    def __init__(self, k, stride, pad=0, pad_hi=None, oob_zero=False):
+        self.k, self.stride, self.pad, self.pad_hi, self.oob_zero = k, stride, pad, pad_hi, oob_zero
 
-    def units(self):
-        us = [self.stem]
-        for b in self.blocks:
-            us += b.all_units()
-        return us
+    def all_units(self):
+        return []
+
+    def forward(self, a_in, tape, training):
+        tape['in_hw'] = (a_in.shape[1], a_in.shape[2])
+        out, tape['argmax'] = ops.maxpool_fwd(a_in, self.k, self.stride, self.pad, self.pad_hi, self.oob_zero)
+        return out
+
+    def backward(self, dout, tape, sink):
+        h, w = tape['in_hw']
+        return ops.maxpool_bwd(dout, tape['argmax'], h, w, self.k, self.stride, self.pad, self.pad_hi)
+
+
+class FcHeadRT:
+    """Global average pool -> nn.Linear (resnet.py:203-204,240-243)."""
+
+    def __init__(self, fc):
+        self.fc = fc
+        self.w_bf16 = None
+        self.b_pad = None
+        self.version = None
 
     def prep(self):
-        for u in self.units():
-            u.prep()
         w = self.fc.weight
         ver = (w.data_ptr(), w._version)
-        if self.fc_w_bf16 is None or ver != self.fc_version:
+        if self.w_bf16 is None or ver != self.version:
             npad = _round_up(w.shape[0], 8)
-            if self.fc_w_bf16 is None:
-                self.fc_w_bf16 = torch.zeros(npad, w.shape[1], device=w.device, dtype=torch.bfloat16)
-                self.fc_b_pad = torch.zeros(npad, device=w.device)
-            ops.cast_bf16(w.detach(), self.fc_w_bf16[:w.shape[0]])
-            self.fc_version = ver
-        self.fc_b_pad[:w.shape[0]].copy_(self.fc.bias.detach())
+            if self.w_bf16 is None:
+                self.w_bf16 = torch.zeros(npad, w.shape[1], device=w.device, dtype=torch.bfloat16)
+                self.b_pad = torch.zeros(npad, device=w.device)
+            ops.cast_bf16(w.detach(), self.w_bf16[:w.shape[0]])
+            self.version = ver
+        self.b_pad[:w.shape[0]].copy_(self.fc.bias.detach())
 
-    # The network is run as three stages (stem / residual blocks / head) so that tests can drive
-    # each stage with the oracle's tensors (tests/test_resnet_gpu.py, teacher-forced parity).
-    def stem_forward(self, x, tape, training):
-        a = self.stem.forward(x, tape['stem'], training)
-        if self.has_maxpool:
-            tape['pool_in_hw'] = (a.shape[1], a.shape[2])
-            a, tape['argmax'] = ops.maxpool3x3s2_fwd(a)
-        return a
-
-    def head_forward(self, a, tape):
+    def forward(self, a, tape):
         tape['feat_hw'] = (a.shape[1], a.shape[2])
         pooled = ops.avgpool_fwd(a)
+        feat = self.fc.weight.shape[1]
+        if pooled.shape[1] != feat:   # channel-padded feature map (e.g. 16/32-channel stacks)
+            pooled = pooled[:, :feat].contiguous()
         tape['pooled'] = pooled
         ncls = self.fc.weight.shape[0]
-        logits = ops.linear_fwd(pooled, self.fc_w_bf16, bias=self.fc_b_pad, out_f32=True)
+        logits = ops.linear_fwd(pooled, self.w_bf16, bias=self.b_pad, out_f32=True)
         if logits.shape[1] != ncls:
             logits = logits[:, :ncls].contiguous()
         return logits
 
-    def forward(self, x, training, keep_tape):
-        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
-        x = x.contiguous()
-        self.prep()
-        tape = {'stem': {}, 'blocks': [dict() for _ in self.blocks]}
-        a = self.stem_forward(x, tape, training)
-        for b, t in zip(self.blocks, tape['blocks']):
-            a = b.forward(a, t, training)
-        logits = self.head_forward(a, tape)
-        self.tape = tape if keep_tape else None
-        return logits
-
-    def head_backward(self, dlogits, tape):
-        """dlogits fp32 [B, num_classes] -> gradient w.r.t. the last feature map (NHWC bf16)."""
-        sink = self.sink
+    def backward(self, dlogits, tape, sink, cpad):
+        """dlogits fp32 [B, num_classes] -> gradient w.r.t. the last feature map (NHWC bf16, cpad channels)."""
         ncls, feat = self.fc.weight.shape
-        npad = self.fc_w_bf16.shape[0]
+        npad = self.w_bf16.shape[0]
         dlogits = dlogits.contiguous().float()
         bbuf, bacc = sink.begin(self.fc.bias)
         ops.colsum(dlogits, bbuf, accumulate=bacc)
@@ -451,9 +430,139 @@ class ResNetRT:
             ops.reduce_partials(part, tmp)
             wbuf.copy_(tmp[:ncls] + (wbuf if wacc else 0))
         sink.done(self.fc.weight, wbuf)
-        dpooled = ops.linear_dgrad(dl, self.fc_w_bf16)
+        dpooled = ops.linear_dgrad(dl, self.w_bf16)
+        if cpad != feat:
+            full = torch.zeros(dpooled.shape[0], cpad, device=dl.device, dtype=torch.bfloat16)
+            full[:, :feat] = dpooled
+            dpooled = full
         h, w = tape['feat_hw']
         return ops.avgpool_bwd(dpooled, h, w)
+
+
+class ConvHeadRT:
+    """Darknet19's classifier (darknet.py:289-297,316-318): 1x1 conv WITH bias, no BN, no activation,
+    then global average pool.  The conv is one GEMM over [N*H*W, C]; classes are padded to a multiple of 8."""
+
+    def __init__(self, conv):
+        self.conv = conv
+        assert conv.kernel_size == (1, 1) and conv.bias is not None
+        self.w_bf16 = None
+        self.b_pad = None
+        self.version = None
+
+    def prep(self):
+        w = self.conv.weight
+        ver = (w.data_ptr(), w._version)
+        if self.w_bf16 is None or ver != self.version:
+            npad = _round_up(w.shape[0], 8)
+            if self.w_bf16 is None:
+                self.w_bf16 = torch.zeros(npad, w.shape[1], device=w.device, dtype=torch.bfloat16)
+                self.b_pad = torch.zeros(npad, device=w.device)
+            ops.cast_bf16(w.detach().view(w.shape[0], w.shape[1]), self.w_bf16[:w.shape[0]])
+            self.version = ver
+        self.b_pad[:w.shape[0]].copy_(self.conv.bias.detach())
+
+    def forward(self, a, tape):
+        n, h, w, c = a.shape
+        tape['a_in'] = a
+        y = ops.linear_fwd(a.view(n * h * w, c), self.w_bf16, bias=self.b_pad)      # bf16 [N*H*W, npad]
+        pooled = ops.avgpool_fwd(y.view(n, h, w, -1))
+        return pooled[:, :self.conv.weight.shape[0]].float()
+
+    def backward(self, dlogits, tape, sink, cpad):
+        a = tape['a_in']
+        n, h, w, c = a.shape
+        ncls = self.conv.weight.shape[0]
+        npad = self.w_bf16.shape[0]
+        dl = torch.zeros(n, npad, device=a.device, dtype=torch.bfloat16)
+        dl[:, :ncls] = dlogits.to(torch.bfloat16)
+        dy = ops.avgpool_bwd(dl, h, w).view(n * h * w, npad)
+        wt, bias = self.conv.weight, self.conv.bias
+        wbuf, wacc = sink.begin(wt)
+        part = ops.linear_wgrad(dy, a.view(n * h * w, c))
+        tmp = torch.empty(npad, c, device=a.device)
+        ops.reduce_partials(part, tmp)
+        g = tmp[:ncls].view_as(wt)
+        wbuf.copy_(g + wbuf if wacc else g)
+        sink.done(wt, wbuf)
+        bbuf, bacc = sink.begin(bias)
+        full = torch.empty(npad, device=a.device)
+        ops.colsum(dy, full)
+        bbuf.copy_(full[:ncls] + bbuf if bacc else full[:ncls])
+        sink.done(bias, bbuf)
+        return ops.linear_dgrad(dy, self.w_bf16).view(n, h, w, c)
+
+
+class ResNetRT:
+    """Whole-network runtime for the conv -> BN -> act classifiers: ResNet (resnet.py:158-245),
+    ResNetCifar (resnetforcifar.py:27-108), DarknetTiny / Darknet19 / Darknet53 (darknet.py:147-432):
+    stem [+ maxpool] + a sequence of stages + head (global average pool + fc, or Darknet19's 1x1-conv
+    classifier + pool).
+
+    checkpoint=True (use_gradient_checkpoint, resnet.py:230-234): the tape keeps only each stage's input;
+    the backward pass re-runs the stage forward before differentiating it, trading one extra forward for
+    the activation memory of all stages.  Like torch.utils.checkpoint in the reference, the replay runs in
+    training mode, so BatchNorm running statistics of the checkpointed stages receive a second momentum
+    update per step (tests/test_reference_semantics_cpu.py pins that behaviour of the reference)."""
+
+    def __init__(self, model, has_maxpool, stem=None, blocks=None, head=None, checkpoint=False):
+        self.model = model
+        self.has_maxpool = has_maxpool
+        if stem is None:
+            stem = ConvBN(model.conv1, ACT_RELU)
+            blocks = []
+            for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
+                for blk in layer:
+                    blocks.append(ResidualBlockRT(blk))
+        self.stem = stem
+        self.blocks = blocks
+        self.head = head if head is not None else FcHeadRT(model.fc)
+        self.checkpoint = checkpoint
+        self.sink = GradSink()
+
+    def units(self):
+        us = [self.stem]
+        for b in self.blocks:
+            us += b.all_units()
+        return us
+
+    def prep(self):
+        for u in self.units():
+            u.prep()
+        self.head.prep()
+
+    # The network is run as three stages (stem / residual blocks / head) so that tests can drive
+    # each stage with the oracle's tensors (tests/test_resnet_gpu.py, teacher-forced parity).
+    def stem_forward(self, x, tape, training):
+        a = self.stem.forward(x, tape['stem'], training)
+        if self.has_maxpool:
+            tape['pool_in_hw'] = (a.shape[1], a.shape[2])
+            a, tape['argmax'] = ops.maxpool3x3s2_fwd(a)
+        return a
+
+    def head_forward(self, a, tape):
+        tape['feat_c'] = a.shape[3]
+        return self.head.forward(a, tape)
+
+    def forward(self, x, training, keep_tape):
+        """Returns (logits, tape); the tape (None unless keep_tape) is what backward() consumes."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+        x = x.contiguous()
+        self.prep()
+        tape = {'stem': {}, 'blocks': [dict() for _ in self.blocks]}
+        a = self.stem_forward(x, tape, training)
+        ckpt = self.checkpoint and keep_tape
+        for b, t in zip(self.blocks, tape['blocks']):
+            if ckpt:
+                t['ckpt_in'] = a
+                a = b.forward(a, {}, training)
+            else:
+                a = b.forward(a, t, training)
+        logits = self.head_forward(a, tape)
+        return logits, (tape if keep_tape else None)
+
+    def head_backward(self, dlogits, tape):
+        return self.head.backward(dlogits, tape, self.sink, tape['feat_c'])
 
     def stem_backward(self, da, tape):
         if self.has_maxpool:
@@ -462,13 +571,15 @@ class ResNetRT:
         dy, _ = self.stem.bn_bwd(da, tape['stem'], self.sink)
         self.stem.conv_bwd(dy, tape['stem'], self.sink, need_dx=False)
 
-    def backward(self, dlogits):
-        tape, sink = self.tape, self.sink
+    def backward(self, dlogits, tape):
+        sink = self.sink
         assert tape is not None, 'backward called without a training forward'
-        self.tape = None
         da = self.head_backward(dlogits, tape)
         for b, t in zip(reversed(self.blocks), reversed(tape['blocks'])):
+            if 'ckpt_in' in t:
+                b.forward(t.pop('ckpt_in'), t, True)
             da = b.backward(da, t, sink)
+            t.clear()
         self.stem_backward(da, tape)
         if sink.on_backward_end is not None:
             sink.on_backward_end()
@@ -477,16 +588,21 @@ class ResNetRT:
 class _NetFunction(torch.autograd.Function):
     """Couples the runtime to autograd: the criterion (torch) differentiates the logits, this
     node receives dlogits and runs the whole backward pass on our kernels.  Parameter gradients
-    are produced as a side effect (GradSink), so no parameter is an autograd input."""
+    are produced as a side effect (GradSink), so no parameter is an autograd input.  The tape of
+    saved activations belongs to THIS forward (it lives on ctx), so several forwards of one module
+    may be in flight before their backwards run."""
 
     @staticmethod
     def forward(ctx, x, anchor, rt):
         ctx.rt = rt
-        return rt.forward(x, True, True)
+        out, ctx.tape = rt.forward(x, True, True)
+        return out
 
     @staticmethod
     def backward(ctx, dlogits):
-        ctx.rt.backward(dlogits)
+        tape, ctx.tape = ctx.tape, None
+        assert tape is not None, 'the graph of this forward pass was already differentiated'
+        ctx.rt.backward(dlogits, tape)
         return None, None, None
 
 
@@ -495,4 +611,4 @@ def run_network(rt, x, training):
         anchor = torch.zeros((), device=x.device, requires_grad=True)
         return _NetFunction.apply(x, anchor, rt)
     with torch.no_grad():
-        return rt.forward(x, training, False)
+        return rt.forward(x, training, False)[0]

@@ -250,6 +250,26 @@ def maxpool3x3s2_bwd(dy, argmax, h, w, out=None):
     return out
 
 
+def maxpool_fwd(x, k, stride, pad=0, pad_hi=None, oob_zero=False):
+    """nn.MaxPool2d(k, stride, pad) on NHWC bf16; pad_hi: padding on the bottom/right edge (defaults to pad);
+    oob_zero: padded taps take part with value 0 (ZeroPad2d + unpadded pool) instead of being ignored."""
+    n, h, w, c = x.shape
+    pad_hi = pad if pad_hi is None else pad_hi
+    P, Q = (h + pad + pad_hi - k) // stride + 1, (w + pad + pad_hi - k) // stride + 1
+    out = torch.empty(n, P, Q, c, device=x.device, dtype=torch.bfloat16)
+    argmax = torch.empty(n, P, Q, c, device=x.device, dtype=torch.uint8)
+    _lib.call('saicv_maxpool_fwd', _p(x), _p(out), _p(argmax), n, h, w, c, k, stride, pad, pad_hi, int(oob_zero), _stream())
+    return out, argmax
+
+
+def maxpool_bwd(dy, argmax, h, w, k, stride, pad=0, pad_hi=None):
+    n, _, _, c = dy.shape
+    pad_hi = pad if pad_hi is None else pad_hi
+    out = torch.empty(n, h, w, c, device=dy.device, dtype=torch.bfloat16)
+    _lib.call('saicv_maxpool_bwd', _p(dy), _p(argmax), _p(out), n, h, w, c, k, stride, pad, pad_hi, _stream())
+    return out
+
+
 def avgpool_fwd(x, out=None):
     n, h, w, c = x.shape
     if out is None:
@@ -293,7 +313,8 @@ def layernorm_bwd(dy, x, gamma, stats, dgamma, dbeta, dres=None, dx=None, dx_bf1
     if dx is None:
         dx = torch.empty(x.shape, device=x.device, dtype=torch.float32)
     _lib.call('saicv_layernorm_bwd', _p(dy), _p(x), _p(gamma), _p(stats), _p(dres), _p(dx), _p(dx_bf16),
-              _p(bf16_row_scale), rows_per_scale, _p(dgamma), _p(dbeta), rows, c, int(accumulate), _stream())
+              _p(bf16_row_scale), rows_per_scale, _p(partial_ws(x.device, 2 * c)), _p(dgamma), _p(dbeta), rows, c,
+              int(accumulate), _stream())
     return dx
 
 

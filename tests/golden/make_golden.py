@@ -1,9 +1,10 @@
-"""Generates tests/golden/*.pt by running the REFERENCE itself (imported from /root/reference)
-in the build container.  The fixtures are small: the seeded input batch, the logits, the loss and
-per-parameter gradient digests (L2 norm + first 4 values); the weights are not stored because
-the oracle reproduces the reference's seeded initialisation exactly (checked here, bit for bit).
+"""Generates tests/golden/*.pt by running the REFERENCE itself (imported from /root/reference, or
+from the baseline/_ref install) in the build container.  The fixtures are small: the seeded input
+batch (or just its seed + a digest for the larger inputs), the logits / feature digest, the loss and
+per-parameter gradient digests (L2 norm + first 4 values); the weights are not stored because the
+oracle reproduces the reference's seeded initialisation exactly (checked here, bit for bit).
 
-    python tests/golden/make_golden.py            # rewrites the fixtures
+    python tests/golden/make_golden.py [tag-substring]     # rewrites the (matching) fixtures
 """
 import os
 import sys
@@ -13,43 +14,109 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, '/root/reference')
+from baseline import ref_import  # noqa: E402
 
+# (tag, family, arch, kwargs, num_classes, batch shape, seed, store_x)
 CASES = [
-    # (tag, arch, num_classes, batch shape, seed)
-    ('resnet18cifar_c100_b8', 'resnet18cifar', 100, (8, 3, 32, 32), 0),  # BASELINE config #1 shape
-    ('resnet50_c1000_b4_64px', 'resnet50', 1000, (4, 3, 64, 64), 0),
-    ('resnet18_c10_b2_64px', 'resnet18', 10, (2, 3, 64, 64), 3),
+    ('resnet18cifar_c100_b8', 'resnet', 'resnet18cifar', {}, 100, (8, 3, 32, 32), 0, True),  # BASELINE config #1 shape
+    ('resnet50_c1000_b4_64px', 'resnet', 'resnet50', {}, 1000, (4, 3, 64, 64), 0, True),
+    ('resnet18_c10_b2_64px', 'resnet', 'resnet18', {}, 10, (2, 3, 64, 64), 3, True),
+    ('vit_base_patch16_c10_b2_64px_cls', 'vit', 'vit_base_patch16', {'image_size': 64, 'global_pool': False}, 10, (2, 3, 64, 64), 4, True),
+    ('vit_base_patch16_c10_b2_64px_gap', 'vit', 'vit_base_patch16', {'image_size': 64, 'global_pool': True}, 10, (2, 3, 64, 64), 4, True),
+    ('vit_base_patch16_c1000_b1_224px_gap', 'vit', 'vit_base_patch16', {'image_size': 224, 'global_pool': True}, 1000, (1, 3, 224, 224), 1, False),
+    ('darknet53_c10_b2_64px', 'darknet', 'darknet53', {}, 10, (2, 3, 64, 64), 2, True),
+    ('darknet19_c10_b2_64px', 'darknet', 'darknet19', {}, 10, (2, 3, 64, 64), 2, True),
+    ('darknettiny_c10_b2_64px', 'darknet', 'darknettiny', {}, 10, (2, 3, 64, 64), 2, True),
+    ('van_b0_c10_b2_64px', 'van', 'van_b0', {}, 10, (2, 3, 64, 64), 6, True),
+    ('van_b1_c10_b1_64px', 'van', 'van_b1', {}, 10, (1, 3, 64, 64), 7, True),
 ]
 
 
+def oracle_init(family, arch, kwargs, nc, seed):
+    """The oracle's seeded initial state for a fixture (shared with tests/test_oracle_golden.py)."""
+    if family == 'resnet':
+        from oracle import convnets
+        return convnets.init_state(arch, nc, seed)
+    if family == 'vit':
+        from oracle import vit
+        return vit.init_state(arch, nc, seed, image_size=kwargs['image_size'])
+    if family == 'darknet':
+        from oracle import darknet
+        return darknet.init_state(nc, seed, arch=arch)
+    if family == 'van':
+        from oracle import van
+        return van.init_state(arch, nc, seed)
+    raise KeyError(family)
+
+
+def oracle_run(family, arch, kwargs, sd, x, y, training=True):
+    """(logits, loss, grads) from the oracle in training mode, or eval logits."""
+    from oracle import train_step
+    if family == 'resnet':
+        from oracle import convnets
+        if training:
+            return train_step.loss_and_grads(sd, x, y, arch)
+        return convnets.forward(sd, x, arch, training=False)
+    if family == 'vit':
+        from oracle import vit
+        if training:
+            return vit.loss_and_grads(sd, x, y, arch, global_pool=kwargs['global_pool'])
+        return vit.forward(sd, x, arch, global_pool=kwargs['global_pool'])
+    if family == 'darknet':
+        from oracle import darknet
+        if training:
+            return darknet.loss_and_grads(sd, x, y, arch=arch)
+        return darknet.forward(sd, x, training=False, arch=arch)
+    if family == 'van':
+        from oracle import van
+        if training:
+            return van.loss_and_grads(sd, x, y, arch)
+        return van.forward(sd, x, arch, training=False)
+    raise KeyError(family)
+
+
+def make_input(shape, nc, seed):
+    g = torch.Generator().manual_seed(1000 + seed)
+    x = torch.randn(*shape, generator=g)
+    y = torch.randint(0, nc, (shape[0],), generator=g)
+    return x, y
+
+
 def main():
-    from SimpleAICV.classification import backbones
-    from SimpleAICV.classification.losses import CELoss
-    from oracle import convnets
+    backbones = ref_import.backbones()
+    CELoss = ref_import.module('SimpleAICV.classification.losses').CELoss
+    only = sys.argv[1] if len(sys.argv) > 1 else ''
     torch.set_num_threads(1)  # fixed reduction order for the recorded numbers
-    for tag, arch, nc, shape, seed in CASES:
+    for tag, family, arch, kwargs, nc, shape, seed, store_x in CASES:
+        if only not in tag:
+            continue
+        try:
+            osd = oracle_init(family, arch, kwargs, nc, seed)
+        except (ImportError, KeyError, TypeError) as e:
+            print(tag, 'skipped (oracle not available yet):', e)
+            continue
         torch.manual_seed(seed)
-        model = backbones.__dict__[arch](num_classes=nc)
+        model = backbones.__dict__[arch](num_classes=nc, **kwargs)
         sd0 = {k: v.clone() for k, v in model.state_dict().items()}
-        osd = convnets.init_state(arch, nc, seed)
+        assert list(sd0.keys()) == list(osd.keys()), 'oracle state_dict keys != reference'
         assert all(torch.equal(sd0[k], osd[k]) for k in sd0), 'oracle init != reference init'
-        g = torch.Generator().manual_seed(1000 + seed)
-        x = torch.randn(*shape, generator=g)
-        y = torch.randint(0, nc, (shape[0],), generator=g)
+        x, y = make_input(shape, nc, seed)
         model.train()
         logits = model(x)
         loss = CELoss()(logits, y)
         loss.backward()
         fix = {
-            'arch': arch, 'num_classes': nc, 'seed': seed, 'x': x, 'y': y,
+            'family': family, 'arch': arch, 'kwargs': kwargs, 'num_classes': nc, 'seed': seed, 'shape': shape, 'y': y,
+            'x_digest': (float(x.double().sum()), x.flatten()[:4].clone()),
             'logits': logits.detach(), 'loss': loss.detach(),
             'grad_norm': {n: p.grad.norm().item() for n, p in model.named_parameters()},
             'grad_head': {n: p.grad.flatten()[:4].clone() for n, p in model.named_parameters()},
-            'running_mean_conv1': model.state_dict()['conv1.layer.1.running_mean'].clone(),
+            'buffers': dict([(k, v.clone()) for k, v in model.state_dict().items() if k.endswith('running_mean')][:2]),
             'torch_version': torch.__version__,
             'reference_commit': '14b1826',
         }
+        if store_x:
+            fix['x'] = x
         model.eval()
         with torch.no_grad():
             fix['eval_logits'] = model(x).clone()

@@ -1,4 +1,4 @@
-"""Darknet-53 on the B200 runtime vs the CPU oracle (oracle/darknet.py): end to end and stage by
+"""DarknetTiny / Darknet19 / Darknet53 on the B200 runtime vs the CPU oracle (oracle/darknet.py): end to end and stage by
 stage with the oracle's boundary tensors (same method and tolerances as tests/test_resnet_gpu.py).
 The 32-channel layers run channel-padded to 64 inside the runtime; only real channels are compared
 and the padded ones must be exactly zero."""
@@ -23,24 +23,28 @@ def _nhwc_padded(t, dtype=torch.bfloat16):
     return t.to(dtype).cuda().contiguous()
 
 
-def _setup(shape, nc=100, seed=0):
+ARCHS = ['darknettiny', 'darknet19', 'darknet53']
+
+
+def _setup(arch, shape, nc=100, seed=0, act_type='leakyrelu'):
     from oracle import darknet
     from simpleaicv_pytorch_training_examples_b200.classification import backbones
     g = torch.Generator().manual_seed(41)
     x = torch.randn(*shape, generator=g)
     y = torch.randint(0, nc, (shape[0],), generator=g)
-    sd = darknet.init_state(nc, seed)
+    sd = darknet.init_state(nc, seed, arch=arch)
     torch.manual_seed(seed)
-    model = backbones.darknet53(num_classes=nc).cuda().train()
+    model = backbones.__dict__[arch](num_classes=nc, act_type=act_type).cuda().train()
     return darknet, sd, model, x, y
 
 
-def test_darknet53_step_matches_oracle():
+@pytest.mark.parametrize('arch,act_type', [(a, 'leakyrelu') for a in ARCHS] + [('darknettiny', 'silu'), ('darknet19', 'relu')])
+def test_darknet_step_matches_oracle(arch, act_type):
     from simpleaicv_pytorch_training_examples_b200.classification import losses
-    darknet, sd, model, x, y = _setup((8, 3, 128, 128))
+    darknet, sd, model, x, y = _setup(arch, (8, 3, 128, 128), act_type=act_type)
     sd32 = {k: v.clone() for k, v in sd.items()}
-    l32, ls32, g32 = darknet.loss_and_grads(sd32, x, y)
-    le, lse, ge = darknet.loss_and_grads(sd, x, y, emulate_bf16=True)
+    l32, ls32, g32 = darknet.loss_and_grads(sd32, x, y, arch=arch, act_type=act_type)
+    le, lse, ge = darknet.loss_and_grads(sd, x, y, emulate_bf16=True, arch=arch, act_type=act_type)
     logits = model(x.cuda())
     loss = losses.CELoss()(logits, y.cuda())
     loss.backward()
@@ -52,15 +56,16 @@ def test_darknet53_step_matches_oracle():
     cat = lambda d: torch.cat([d[n].flatten() for n in g32])
     mine_all, emu_all = _rel_l2(cat(grads), cat(g32)), _rel_l2(cat(ge), cat(g32))
     assert mine_all <= 2.0 * emu_all + 5e-2, (mine_all, emu_all)
-    rm = model.state_dict()['conv1.layer.1.running_mean'].cpu()
-    torch.testing.assert_close(rm, sd['conv1.layer.1.running_mean'], rtol=1e-2, atol=1e-3)
-    print(f'darknet53: logits rel L2 {_rel_l2(logits.detach(), le):.4g}; whole-gradient rel L2 to fp32 {mine_all:.4g} (storage noise {emu_all:.4g})')
+    k0 = next(k for k in sd if k.endswith('running_mean'))
+    torch.testing.assert_close(model.state_dict()[k0].cpu(), sd[k0], rtol=1e-2, atol=1e-3)
+    print(f'{arch}/{act_type}: logits rel L2 {_rel_l2(logits.detach(), le):.4g}; whole-gradient rel L2 to fp32 {mine_all:.4g} (storage noise {emu_all:.4g})')
 
 
-def test_darknet53_stagewise_parity_with_oracle_tensors():
-    darknet, sd, model, x, y = _setup((8, 3, 128, 128))
+@pytest.mark.parametrize('arch', ARCHS)
+def test_darknet_stagewise_parity_with_oracle_tensors(arch):
+    darknet, sd, model, x, y = _setup(arch, (8, 3, 128, 128))
     trace = {}
-    _, _, ge = darknet.loss_and_grads(sd, x, y, emulate_bf16=True, trace=trace)
+    _, _, ge = darknet.loss_and_grads(sd, x, y, emulate_bf16=True, trace=trace, arch=arch)
     names = {id(p): n for n, p in model.named_parameters()}
     rt = model._runtime()
     rt.prep()
@@ -109,7 +114,10 @@ def test_darknet53_stagewise_parity_with_oracle_tensors():
     grad_close(logits, trace['logits'].detach(), 'logits', 2e-2)
     da = rt.head_backward(trace['logits'].grad.cuda(), tape)
     grad_close(da, trace[prev].grad.permute(0, 2, 3, 1), 'head input gradient', 2e-2)
-    grad_close(model.fc.weight.grad, ge['fc.weight'], 'fc.weight', 2e-2)
+    hw = 'layer7.layer.0.weight' if arch == 'darknet19' else 'fc.weight'
+    grad_close(dict(model.named_parameters())[hw].grad, ge[hw], hw, 2e-2)
+    hb = hw.replace('weight', 'bias')
+    grad_close(dict(model.named_parameters())[hb].grad, ge[hb], hb, 2e-2)
     torch.cuda.synchronize()
-    print(f'darknet53 stagewise: worst {max(report)}')
+    print(f'{arch} stagewise: worst {max(report)}')
     assert not failures, f'{len(failures)} stage checks failed: ' + '; '.join(failures[:12])
