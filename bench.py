@@ -1,23 +1,25 @@
 #!/usr/bin/env python
 """bench.py — images/sec of the SimpleAICV classification training step on B200.
 
-Workload (BASELINE.json configs[1]): ResNet-50, 224x224, batch 256 per GPU, synthetic images,
+Headline workload (BASELINE.json configs[1]): ResNet-50, 224x224, batch 256 per GPU, synthetic images,
 CELoss, SGD(lr 0.1, momentum 0.9, wd 1e-4, 1-D params undecayed) — one "step" is forward + loss +
 backward (+ bucketed gradient all-reduce when N > 1) + optimizer step, exactly the work of
-tools/scripts.py:141-270 in the reference.
+tools/scripts.py:141-270 in the reference.  The same JSON line carries a ``vit_base_patch16`` sub-record
+(BASELINE configs[2]: ViT-B/16, soft labels, AdamW with layer-wise lr decay) measured the same way.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (sm_100a kernels)
-  python bench.py --impl reference ...                           reference arm: the CPU oracle
-                                                                 (oracle/, restating the reference)
+  python bench.py [--gpus N] [--steps K] [--warmup W]     our arm (sm_100a kernels)
+  python bench.py --impl reference ...                    reference arm: the reference's CPU path (its own
+                                                          modules from baseline/_ref, else the oracle port)
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what every key means.
 """
 import argparse
+import contextlib
 import json
 import os
+import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -28,6 +30,8 @@ import torch.distributed as dist  # noqa: E402
 
 METRICS = {'resnet50': 'images/sec (ResNet-50 224x224 training step, whole job)',
            'vit_base_patch16': 'images/sec (ViT-B/16 224x224 training step, whole job)'}
+WORKLOADS = {'resnet50': 'ResNet-50 224x224 bs256/GPU training step (fwd+CELoss+bwd+grad all-reduce+SGD)',
+             'vit_base_patch16': 'ViT-B/16 224x224 bs256/GPU training step (fwd+OneHotLabelCELoss+bwd+grad all-reduce+AdamW)'}
 FWD_FLOPS = {'resnet50': 8.178e9, 'vit_base_patch16': 35.13e9}   # per image forward; a step is 3x
 ALGO_BYTES = {'resnet50': 130e6, 'vit_base_patch16': 3 * 65e6}  # per image per step, activations once each way (8d)
 
@@ -39,6 +43,13 @@ def _peaks():
         return {'hbm_gbs': d['hbm_gbs'], 'tf_burst': d['bf16_tflops'], 'tf_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']),
                 'source': 'measured'}
     return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'source': 'fallback'}
+
+
+def _traffic():
+    """DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r02_traffic.json, written by tests/summarize_profiles.py from the .ncu-rep)."""
+    p = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    return json.load(open(p)) if os.path.exists(p) else None
 
 
 class ClockSampler:
@@ -84,55 +95,138 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def build_optimizer(model, lr=0.1, momentum=0.9, weight_decay=1e-4):
-    """tools/utils.py:292-600 with global_weight_decay=False (imagenet/resnet50/train_config.py:66-79)."""
-    decay = [p for p in model.parameters() if p.ndim > 1]
-    no_decay = [p for p in model.parameters() if p.ndim <= 1]
-    return torch.optim.SGD([{'params': decay, 'weight_decay': weight_decay}, {'params': no_decay, 'weight_decay': 0.0}],
-                           lr=lr, momentum=momentum)
+def vit_optimizer_cfg(model):
+    class _Cfg:
+        optimizer = ('AdamW', {'lr': 5e-4, 'global_weight_decay': False, 'weight_decay': 0.05,
+                               'no_weight_decay_layer_name_list': ['position_encoding', 'cls_token'],
+                               'lr_layer_decay': 0.65, 'lr_layer_decay_block': model.blocks, 'block_name': 'blocks'})
+    return _Cfg
+
+
+def r50_optimizer_cfg():
+    class _Cfg:
+        optimizer = ('SGD', {'lr': 0.1, 'momentum': 0.9, 'global_weight_decay': False, 'weight_decay': 1e-4,
+                             'no_weight_decay_layer_name_list': []})
+    return _Cfg
+
+
+def synthetic_batch(model_name, B, rank, pin):
+    g = torch.Generator().manual_seed(1234 + rank)
+    x = torch.randn(B, 3, 224, 224, generator=g)
+    if model_name == 'resnet50':
+        y = torch.randint(0, 1000, (B,), generator=g)
+    else:  # mixup-style soft labels
+        lab = torch.randint(0, 1000, (B,), generator=g)
+        oh = torch.nn.functional.one_hot(lab, 1000).float() * 0.9 + 0.1 / 1000
+        y = 0.5 * oh + 0.5 * oh.roll(1, 0)
+    return (x.pin_memory(), y.pin_memory()) if pin else (x, y)
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_oracle_images_per_sec(model, batch, steps, threads):
-    """The reference's CPU path (its model code restated by oracle/) on this box's host cores."""
-    from oracle import convnets, train_step, vit
+def cpu_reference_step_times(model_name, batch, warmup, steps, threads):
+    """The reference's CPU path on this box's host cores: the UNMODIFIED reference modules (baseline/_ref;
+    model, criterion and tools.utils.build_optimizer) driven through the arithmetic of one
+    tools/scripts.py:141-270 step in fp32 (its entry points hard-require CUDA/NCCL).
+    Falls back to the oracle port when the reference install is absent.  Returns (kind, [seconds per step])."""
     torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(batch, 3, 224, 224, generator=g)
-    y = torch.randint(0, 1000, (batch,), generator=g)
-    sd = convnets.init_state('resnet50', 1000, 0) if model == 'resnet50' else vit.init_state(model, 1000, 0)
-    buf = {}
-    times = []
-    for i in range(steps + 1):
-        t0 = time.perf_counter()
-        if model == 'resnet50':
-            _, _, grads = train_step.loss_and_grads(sd, x, y, 'resnet50')
+    _retain_freed_host_memory()
+    x, y = synthetic_batch(model_name, batch, 0, False)
+    from baseline import ref_import
+    if ref_import.available():
+        kind = 'reference'
+        backbones = ref_import.backbones()
+        ref_losses = ref_import.module('SimpleAICV.classification.losses')
+        ref_utils = ref_import.module('tools.utils')
+        torch.manual_seed(0)
+        if model_name == 'resnet50':
+            model, crit = backbones.resnet50(num_classes=1000), ref_losses.CELoss()
+            opt, _ = ref_utils.build_optimizer(r50_optimizer_cfg(), model)
         else:
-            _, _, grads = vit.loss_and_grads(sd, x, y, model, global_pool=True)
-        train_step.sgd_step(sd, grads, buf, 0.1)  # the CPU cost of the parameter update is negligible either way
-        if i > 0:
+            model = backbones.vit_base_patch16(image_size=224, num_classes=1000, drop_path_prob=0.1, global_pool=True)
+            crit = ref_losses.OneHotLabelCELoss()
+            opt, _ = ref_utils.build_optimizer(vit_optimizer_cfg(model), model)
+        model.train()
+
+        def step():
+            loss = crit(model(x), y)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            return loss.item()
+    else:
+        kind = 'port'
+        from oracle import convnets, train_step, vit
+        sd = convnets.init_state('resnet50', 1000, 0) if model_name == 'resnet50' else vit.init_state(model_name, 1000, 0)
+        buf = {}
+
+        def step():
+            if model_name == 'resnet50':
+                _, loss, grads = train_step.loss_and_grads(sd, x, y, 'resnet50')
+            else:
+                _, loss, grads = vit.loss_and_grads(sd, x, y, model_name, global_pool=True)
+            train_step.sgd_step(sd, grads, buf, 0.1)
+            return float(loss)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        step()
+        if i >= warmup:
             times.append(time.perf_counter() - t0)
-    dt = sum(times) / len(times)
-    return batch / dt, dt
+    return kind, times
+
+
+def _retain_freed_host_memory():
+    """glibc returns the multi-GB activation buffers of every CPU step to the kernel and page-faults them
+    back in on the next one (round 1: 22x run-to-run spread, most of it system time).  Raising the
+    trim / mmap thresholds keeps freed blocks in the process, which makes step times repeatable
+    (measured here: 1.5-4.3 s/step -> 1.0-1.3 s/step for ResNet-50 batch 16 on 8 cores)."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL('libc.so.6')
+        libc.mallopt(-1, 2 ** 31 - 1)   # M_TRIM_THRESHOLD
+        libc.mallopt(-3, 2 ** 31 - 1)   # M_MMAP_THRESHOLD
+    except Exception:
+        pass
+
+
+def host_threads():
+    """min(32, physical cores): more threads than that made the fp32 CPU step slower and unstable in round 1
+    (0.4 .. 9 img/s on 128 logical cores)."""
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+    except Exception:
+        phys = os.cpu_count() or 1
+    return max(1, min(32, phys)), phys
+
+
+def cpu_baseline_record(model_name, batch, warmup, steps):
+    threads, phys = host_threads()
+    kind, times = cpu_reference_step_times(model_name, batch, warmup, steps, threads)
+    med, best = statistics.median(times), min(times)
+    return {'value': batch / med, 'unit': 'images/s', 'cores': threads, 'kind': kind,
+            'value_best': batch / best, 'sec_per_step_median': med, 'sec_per_step_min': best,
+            'sample': (f'{steps} timed steps of batch {batch} after {warmup} warm-ups of the same {model_name} training step '
+                       f'(fwd+loss+bwd+optimizer), fp32, {"unmodified reference modules (baseline/_ref)" if kind == "reference" else "oracle port"}, '
+                       f'torch {torch.__version__} CPU, {threads} threads on {phys} physical cores; median reported'),
+            'physical_cores': phys}
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's own CPU implementation of the step, all host threads."""
+    """--impl reference: the reference's own CPU implementation of the step (rank 0 only)."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
     batch = 16
-    steps = max(1, min(args.steps, 3))
-    ips, dt = cpu_oracle_images_per_sec(args.model, batch, steps, cores)
+    warmup, steps = max(2, min(args.warmup, 3)), max(5, min(args.steps, 8))
+    cb = cpu_baseline_record(args.model, batch, warmup, steps)
     line = {
-        'impl': 'reference', 'metric': METRICS[args.model], 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
-        'warmup': 1, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'impl': 'reference', 'metric': METRICS[args.model], 'value': cb['value'], 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': warmup, 'ms_per_step': cb['sec_per_step_median'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.model} 224x224 training step, reference model code on CPU',
-                   'per_step_batch': batch},
-        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{steps} timed steps of batch {batch} (1 warm-up), fp32, torch {torch.__version__} CPU'},
-        'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'config': {'workload': WORKLOADS[args.model] + ' — bounded CPU sample: one process, batch 16 per step',
+                   'per_step_batch': batch, 'same_step_arithmetic': True},
+        'cpu_baseline': cb,
+        'e2e': {'value': cb['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -146,7 +240,8 @@ class OpTimer:
 
     def install(self):
         from simpleaicv_pytorch_training_examples_b200 import _lib
-        self._lib = _lib
+        import simpleaicv_pytorch_training_examples_b200.ops as ops
+        self._lib, self._ops = _lib, ops
         self._orig = _lib.call
         timer = self
 
@@ -159,13 +254,13 @@ class OpTimer:
             return rc
 
         _lib.call = timed
-        import simpleaicv_pytorch_training_examples_b200.ops as ops
         ops._lib.call = timed
 
     def remove(self):
         self._lib.call = self._orig
+        self._ops._lib.call = self._orig
 
-    def summarize(self, batch):
+    def summarize(self):
         torch.cuda.synchronize()
         out = {}
         for name, a, s, e in self.records:
@@ -179,8 +274,7 @@ class OpTimer:
 
 
 def _cs(a):
-    cs = a._obj if hasattr(a, '_obj') else a
-    return cs
+    return a._obj if hasattr(a, '_obj') else a
 
 
 def describe(name, a):
@@ -206,41 +300,95 @@ def describe(name, a):
     if name == 'saicv_linear_wgrad':    # (dy, x, dw, M, N, K, splits, stream)
         M, N, K = a[-5], a[-4], a[-3]
         return f'linear_wgrad M{M} N{N} K{K}', 2.0 * M * N * K, 2.0 * (M * K + M * N) + 4.0 * N * K
+    if name in ('saicv_attention_fwd', 'saicv_attention_bwd'):   # (..., b, l, h, d, scale, stream) + optional extras
+        b, l, h, d = a[-6], a[-5], a[-4], a[-3]
+        mult = 2 if name.endswith('fwd') else 5                  # QK^T, PV | + dP, dQ, dK, dV (S recomputed)
+        io = (4 if name.endswith('fwd') else 9) * b * l * h * d * 2
+        return f'{name[6:]} B{b} L{l} H{h} D{d}', mult * 2.0 * b * h * l * l * d, float(io)
     return name[6:], 0.0, 0.0
 
 
-def run_b200(args, rank, world, local_rank):
+def roofline_from_table(table, peaks, model_name, B, ms_step, dump_path=None):
+    """All-launch roofline of the tensor-core engine kernels of one step (gemm_sm100_kernel + the attention
+    kernels): every launch is bounded by max(FLOPs / tensor peak, algorithmic bytes / HBM peak); frac =
+    sum of those roofline times / sum of the measured CUDA-event times.  The two classes are kept beside it."""
+    gemm = {k: v for k, v in table.items() if v['flops'] > 0}
+    tf_peak, bw_peak = peaks['tf_sustained'] * 1e12, peaks['hbm_gbs'] * 1e9
+    cls = {'tensor': {'work': 0.0, 'ms': 0.0, 'roof_ms': 0.0, 'launches': 0},
+           'hbm': {'work': 0.0, 'ms': 0.0, 'roof_ms': 0.0, 'launches': 0}}
+    for k, v in gemm.items():
+        t_t, t_h = v['flops'] / tf_peak * 1e3, v['bytes'] / bw_peak * 1e3
+        c = cls['tensor'] if t_t >= t_h else cls['hbm']
+        c['work'] += v['flops'] if t_t >= t_h else v['bytes']
+        c['ms'] += v['ms']
+        c['roof_ms'] += max(t_t, t_h)
+        c['launches'] += v['calls']
+        v['roof_frac'] = max(t_t, t_h) / v['ms'] if v['ms'] else 0.0
+    gemm_ms = sum(v['ms'] for v in gemm.values())
+    all_ms = sum(v['ms'] for v in table.values())
+    dom = 'tensor' if cls['tensor']['ms'] >= cls['hbm']['ms'] else 'hbm'
+    frac_all = sum(c['roof_ms'] for c in cls.values()) / gemm_ms if gemm_ms else 0.0
+
+    def cls_rec(k):
+        c = cls[k]
+        if not c['ms']:
+            return None
+        ach = c['work'] / (c['ms'] / 1e3) / (1e12 if k == 'tensor' else 1e9)
+        peak = peaks['tf_sustained'] if k == 'tensor' else peaks['hbm_gbs']
+        return {'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s' if k == 'tensor' else 'GB/s', 'frac': ach / peak,
+                'launches': c['launches'], 'share_of_engine_time': c['ms'] / gemm_ms}
+    d = cls_rec(dom)
+    worst = min(gemm, key=lambda k: gemm[k]['roof_frac']) if gemm else None
+    top = max(gemm, key=lambda k: gemm[k]['ms']) if gemm else None
+    tr = _traffic()
+    roof = {'bound': dom, 'achieved': d['achieved'] * frac_all / d['frac'] if d and d['frac'] else None, 'peak': d['peak'] if d else None,
+            'unit': d['unit'] if d else None, 'frac': frac_all,
+            'traffic': (tr or {}).get(model_name, {}).get('dram_bytes_per_launch'),
+            'traffic_note': (tr or {}).get(model_name, {}).get('note'),
+            'kernel': 'gemm_sm100_kernel (+ attention kernels for ViT)',
+            'frac_definition': ('ALL launches of the tensor-core engine in one step: each launch is bounded by max(algorithmic '
+                                'FLOPs / sustained bf16 peak, algorithmic bytes / HBM peak) from MEASURED_PEAKS; frac = sum(bound '
+                                'times) / sum(CUDA-event times).  achieved/peak/unit restate frac in the units of the class that '
+                                'holds most of the time; per-class figures are under classes.'),
+            'peak_source': peaks['source'],
+            'classes': {k: cls_rec(k) for k in cls},
+            'slowest_launch': ({'launch': top, 'ms_per_launch': gemm[top]['ms'] / gemm[top]['calls'],
+                                'frac_of_its_roofline': gemm[top]['roof_frac']} if top else None),
+            'worst_launch': ({'launch': worst, 'frac_of_its_roofline': gemm[worst]['roof_frac'],
+                              'ms_per_step': gemm[worst]['ms']} if worst else None),
+            'engine_share_of_step': gemm_ms / all_ms if all_ms else None,
+            'step_tensor_tflops': 3 * FWD_FLOPS[model_name] * B / (ms_step / 1e3) / 1e12,
+            'step_hbm_gbs_algorithmic': ALGO_BYTES[model_name] * B / (ms_step / 1e3) / 1e9,
+            'step_frac_of_network_roofline': max(3 * FWD_FLOPS[model_name] * B / tf_peak, ALGO_BYTES[model_name] * B / bw_peak) * 1e3 / ms_step}
+    if dump_path:
+        rows = sorted(table.items(), key=lambda kv: -kv[1]['ms'])
+        with open(dump_path, 'w') as f:
+            f.write('op,calls,ms_per_step,GFLOP,algorithmic_MB,TFLOP/s,GB/s,frac_of_roofline\n')
+            for k, v in rows:
+                s = v['ms'] / 1e3
+                f.write(f"{k},{v['calls']},{v['ms']:.4f},{v['flops'] / 1e9:.2f},{v['bytes'] / 1e6:.2f},"
+                        f"{v['flops'] / s / 1e12 if s else 0:.1f},{v['bytes'] / s / 1e9 if s else 0:.1f},{v.get('roof_frac', 0):.3f}\n")
+    return roof
+
+
+def measure_model(model_name, args, rank, world, local_rank, dump_path=None, with_ddp_check=False):
+    """Device-timed and end-to-end throughput + the roofline pass for one model.  Returns a dict (rank 0) or None."""
     from simpleaicv_pytorch_training_examples_b200 import _lib
     from simpleaicv_pytorch_training_examples_b200.classification import backbones, losses
-    from simpleaicv_pytorch_training_examples_b200.distributed import B200DataParallel
+    from simpleaicv_pytorch_training_examples_b200.distributed import B200DataParallel, overlap_self_check
+    from simpleaicv_pytorch_training_examples_b200.tools import utils as tutils
     dev = torch.device('cuda', local_rank)
-    torch.cuda.set_device(dev)
     B = args.batch
     torch.manual_seed(0)
-    g = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
-    if args.model == 'resnet50':
+    x_host, y_host = synthetic_batch(model_name, B, rank, True)
+    if model_name == 'resnet50':
         model = backbones.resnet50(num_classes=1000).to(dev).train()
         crit = losses.CELoss().to(dev)
-        opt = build_optimizer(model)
-        y_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
-        workload = 'ResNet-50 224x224 bs256/GPU training step (fwd+CELoss+bwd+grad all-reduce+SGD)'
+        opt, _ = tutils.build_optimizer(r50_optimizer_cfg(), model)
     else:
-        # BASELINE configs[2] / SURVEY.md 8d C3: vit_base_patch16(global_pool, drop_path 0.1), soft labels,
-        # OneHotLabelCELoss, AdamW(5e-4, wd .05) with layer-wise lr decay .65
-        from simpleaicv_pytorch_training_examples_b200.tools import utils as tutils
         model = backbones.vit_base_patch16(image_size=224, num_classes=1000, drop_path_prob=0.1, global_pool=True).to(dev).train()
         crit = losses.OneHotLabelCELoss().to(dev)
-
-        class _Cfg:
-            optimizer = ('AdamW', {'lr': 5e-4, 'global_weight_decay': False, 'weight_decay': 0.05,
-                                   'no_weight_decay_layer_name_list': ['position_encoding', 'cls_token'],
-                                   'lr_layer_decay': 0.65, 'lr_layer_decay_block': model.blocks, 'block_name': 'blocks'})
-        opt, _ = tutils.build_optimizer(_Cfg, model)
-        lab = torch.randint(0, 1000, (B,), generator=g)
-        one_hot = torch.nn.functional.one_hot(lab, 1000).float() * 0.9 + 0.1 / 1000
-        y_host = (0.5 * one_hot + 0.5 * one_hot.roll(1, 0)).pin_memory()
-        workload = 'ViT-B/16 224x224 bs256/GPU training step (fwd+OneHotLabelCELoss+bwd+grad all-reduce+AdamW)'
+        opt, _ = tutils.build_optimizer(vit_optimizer_cfg(model), model)
     net = B200DataParallel(model) if world > 1 else model
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
@@ -269,8 +417,21 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(3, args.warmup)):
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         step(x_dev, y_dev)
+    ddp_check = None
+    if world > 1 and with_ddp_check:
+        # bit-exactness of the overlapped bucket all-reduce vs no_sync + reduce_now on the same batch
+        # (drop-path masks are reseeded so that both passes draw the same ones)
+        def fb():
+            torch.manual_seed(77)
+            crit(net(x_dev), y_dev).backward()
+        ndiff = torch.tensor([overlap_self_check(net, fb)], device=dev)
+        dist.all_reduce(ndiff, op=dist.ReduceOp.SUM)
+        ddp_check = 'ok: overlapped all-reduce bit-identical to no_sync+reduce_now on every rank' if int(ndiff) == 0 \
+            else f'FAILED: {int(ndiff)} gradient elements differ'
+        opt.zero_grad()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -283,119 +444,78 @@ def run_b200(args, rank, world, local_rank):
     # end to end through the public API: every step's batch comes from pinned host memory through
     # tools.utils.CudaPrefetcher (the loader wrapper train_classification uses: H2D of batch i+1 on a
     # side stream while step i computes) and the loss is read back to the host every step
-    from simpleaicv_pytorch_training_examples_b200.tools.utils import CudaPrefetcher
-
     def e2e_loop(k):
         host_batches = ({'image': x_host, 'label': y_host} for _ in range(k))
-        for batch in CudaPrefetcher(host_batches, dev):
+        for batch in tutils.CudaPrefetcher(host_batches, dev):
             step(batch['image'], batch['label']).item()
 
     e2e_loop(2)
-    barrier()
-    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s_.record()
-    e2e_loop(args.steps)
-    e_.record()
-    barrier()
-    t_ = torch.tensor([s_.elapsed_time(e_)], device=dev)
-    if world > 1:
-        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t_.item()) / args.steps
+    e2e_ms = timed(lambda: e2e_loop(args.steps), 1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
-    e2e_value = B * world / (e2e_ms / 1e3)
-
-    roof, cpu_base, table = None, None, None
-    peaks = _peaks()
+    rec = None
     if rank == 0:
         # instrumented pass (not part of any reported throughput): per-op CUDA-event timing
         # (rank 0 only: the gradient exchange is skipped, otherwise the other ranks would be waited for)
-        import contextlib
         t = OpTimer()
         t.install()
         with (net.no_sync() if world > 1 else contextlib.nullcontext()):
             for _ in range(2):
                 step(x_dev, y_dev)
-        table = t.summarize(B)
+        table = t.summarize()
         t.remove()
         for d in table.values():
             d['ms'] /= 2
             d['calls'] //= 2
             d['flops'] /= 2
             d['bytes'] /= 2
-        gemm = {k: v for k, v in table.items() if v['flops'] > 0}
-        # Dominant kernel = gemm_sm100_kernel (every conv / linear fprop, dgrad, wgrad launch of the step).
-        # Each launch is bound either by the tensor pipe or by HBM (algorithmic FLOPs and bytes of its
-        # shape); per class: achieved = sum(algorithmic work) / sum(CUDA-event durations).
-        tf_peak, bw_peak = peaks['tf_sustained'] * 1e12, peaks['hbm_gbs'] * 1e9
-        cls = {'tensor': {'work': 0.0, 'ms': 0.0, 'roof_ms': 0.0, 'launches': 0},
-               'hbm': {'work': 0.0, 'ms': 0.0, 'roof_ms': 0.0, 'launches': 0}}
-        for k, v in gemm.items():
-            t_t, t_h = v['flops'] / tf_peak * 1e3, v['bytes'] / bw_peak * 1e3
-            c = cls['tensor'] if t_t >= t_h else cls['hbm']
-            c['work'] += v['flops'] if t_t >= t_h else v['bytes']
-            c['ms'] += v['ms']
-            c['roof_ms'] += max(t_t, t_h)
-            c['launches'] += v['calls']
-            v['roof_frac'] = max(t_t, t_h) / v['ms'] if v['ms'] else 0.0
-        dom = 'tensor' if cls['tensor']['ms'] >= cls['hbm']['ms'] else 'hbm'
-        d = cls[dom]
-        if dom == 'tensor':
-            ach, peak, unit = d['work'] / (d['ms'] / 1e3) / 1e12, peaks['tf_sustained'], 'TFLOP/s'
-        else:
-            ach, peak, unit = d['work'] / (d['ms'] / 1e3) / 1e9, peaks['hbm_gbs'], 'GB/s'
-        gemm_ms = sum(v['ms'] for v in gemm.values())
-        all_ms = sum(v['ms'] for v in table.values())
-        top_key = max(gemm, key=lambda k: gemm[k]['ms'])
-        roof = {'bound': dom, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak, 'traffic': None,
-                'kernel': 'gemm_sm100_kernel', 'launches_in_class': d['launches'],
-                'frac_definition': ('every gemm_sm100_kernel launch of the step is classed tensor- or hbm-bound from its '
-                                    'algorithmic FLOPs / bytes vs MEASURED_PEAKS; achieved = sum(work) / sum(CUDA-event time) '
-                                    'over the class holding most of the GEMM time; frac = achieved / peak of that class. '
-                                    'See other_class, all_launches_frac_of_roofline_time and slowest_launch for the rest.'),
-                'definition_changed_from': ('earlier lines of this round reported the single (op, shape) with the largest total '
-                                            'time (R50: conv_wgrad 3x3 c64 k64 56x56, frac ~0.145); that launch is still '
-                                            'reported under slowest_launch and did not get faster'),
-                'peak_source': peaks['source'] + (' (sustained)' if dom == 'tensor' else ''),
-                'class_share_of_gemm_time': d['ms'] / gemm_ms,
-                'all_launches_frac_of_roofline_time': sum(c['roof_ms'] for c in cls.values()) / gemm_ms,
-                'other_class': {k: (c['work'] / (c['ms'] / 1e3) / (1e12 if k == 'tensor' else 1e9) if c['ms'] else None)
-                                for k, c in cls.items() if k != dom},
-                'slowest_launch': {'launch': top_key, 'ms_per_launch': gemm[top_key]['ms'] / gemm[top_key]['calls'],
-                                   'frac_of_its_roofline': gemm[top_key]['roof_frac']},
-                'gemm_share_of_step': gemm_ms / all_ms if all_ms else None,
-                'step_tensor_tflops': 3 * FWD_FLOPS[args.model] * B / (ms_step / 1e3) / 1e12,
-                'step_hbm_gbs_algorithmic': ALGO_BYTES[args.model] * B / (ms_step / 1e3) / 1e9}
-        if args.dump_ops:
-            rows = sorted(table.items(), key=lambda kv: -kv[1]['ms'])
-            with open(args.dump_ops, 'w') as f:
-                f.write('op,calls,ms_per_step,GFLOP,algorithmic_MB,TFLOP/s,GB/s,frac_of_roofline\n')
-                for k, v in rows:
-                    s = v['ms'] / 1e3
-                    f.write(f"{k},{v['calls']},{v['ms']:.4f},{v['flops'] / 1e9:.2f},{v['bytes'] / 1e6:.2f},"
-                            f"{v['flops'] / s / 1e12 if s else 0:.1f},{v['bytes'] / s / 1e9 if s else 0:.1f},{v.get('roof_frac', 0):.3f}\n")
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            ips, dt = cpu_oracle_images_per_sec(args.model, 8, 2, cores)
-            cpu_base = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                        'sample': f'2 timed steps of batch 8 (1 warm-up) of the same {args.model} step, fp32 oracle, {dt:.2f} s/step'}
+        roof = roofline_from_table(table, _peaks(), model_name, B, ms_step, dump_path)
+        rec = {'metric': METRICS[model_name], 'value': value, 'unit': 'images/s', 'ms_per_step': ms_step,
+               'e2e': {'value': B * world / (e2e_ms / 1e3), 'unit': 'images/s', 'ms_per_step': e2e_ms,
+                       'h2d_bytes_per_step': (x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()) * world,
+                       'd2h_bytes_per_step': 4 * world},
+               'gpu_launches': int(launches), 'roofline': roof, 'clocks': clocks, 'workload': WORKLOADS[model_name],
+               'ddp_check': ddp_check}
+    del model, net, opt
+    torch.cuda.empty_cache()
+    return rec
 
-    if rank == 0:
-        line = {
-            'metric': METRICS[args.model], 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
-            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
-            'data': 'synthetic',
-            'config': {'workload': workload,
-                       'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': f'dp{world}',
-                       'l2_policy': 'inputs+activations (>10 GB/step) far exceed the 126 MB L2; no explicit flush',
-                       'images_per_sec_per_gpu': value / world},
-            'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': 'images/s', 'ms_per_step': e2e_ms,
-                    'h2d_bytes_per_step': (x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()) * world, 'd2h_bytes_per_step': 4 * world},
-            'gpu_launches': int(launches),
-            'roofline': roof,
-            'cpu_baseline': cpu_base,
-        }
-        print(json.dumps(line), flush=True)
+
+def run_b200(args, rank, world, local_rank):
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    B = args.batch
+    main = measure_model(args.model, args, rank, world, local_rank, args.dump_ops, with_ddp_check=True)
+    other = None
+    if not args.no_second_model:
+        second = 'vit_base_patch16' if args.model == 'resnet50' else 'resnet50'
+        other = measure_model(second, args, rank, world, local_rank,
+                              args.dump_ops.replace('.csv', f'_{second}.csv') if args.dump_ops else None)
+    if rank != 0:
+        return
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_record(args.model, 16, 2, 5)
+    line = {
+        'metric': main['metric'], 'value': main['value'], 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(3, args.warmup), 'ms_per_step': main['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': main['workload'], 'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': f'dp{world}',
+                   'l2_policy': 'inputs+activations (>10 GB/step) far exceed the 126 MB L2; no explicit flush',
+                   'images_per_sec_per_gpu': main['value'] / world},
+        'clocks': main['clocks'], 'e2e': main['e2e'], 'gpu_launches': main['gpu_launches'], 'roofline': main['roofline'],
+        'cpu_baseline': cpu_base,
+    }
+    if main.get('ddp_check'):
+        line['ddp_check'] = main['ddp_check']
+    if other is not None:
+        name = 'vit_base_patch16' if args.model == 'resnet50' else 'resnet50'
+        line[name] = {k: other[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'e2e', 'gpu_launches', 'roofline', 'clocks', 'workload')}
+        line[name]['images_per_sec_per_gpu'] = other['value'] / world
+    torch_base = os.path.join(ROOT, 'profiles', 'r02_torch_gpu_baseline.json')
+    if os.path.exists(torch_base):
+        line['torch_ddp_target'] = {'source': 'profiles/r02_torch_gpu_baseline.json (unmodified reference under torch DDP, same pool)',
+                                    'records': json.load(open(torch_base)).get('summary')}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -409,6 +529,7 @@ def main():
                     help='resnet50 = BASELINE configs[1] (default, the headline); vit_base_patch16 = configs[2]')
     ap.add_argument('--dump-ops', default=None, help='write the per-op timing table (csv) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-second-model', action='store_true', help='skip the sub-record of the other BASELINE model')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -417,7 +538,7 @@ def main():
         run_reference(args, rank)
         return
     if not torch.cuda.is_available():
-        raise SystemExit('bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU oracle)')
+        raise SystemExit('bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU path)')
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         torch.cuda.set_device(local_rank)

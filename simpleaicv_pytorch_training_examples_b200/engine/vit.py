@@ -142,7 +142,6 @@ class ViTRT:
         self.blocks = [_Block(b) for b in model.blocks]
         self.fc = _Linear(model.fc)
         self.sink = GradSink()
-        self.tape = None
         self.pw_bf16 = None
         self.pw_version = None
 
@@ -193,8 +192,7 @@ class ViTRT:
         for blk, t in zip(self.blocks, tape['blocks']):
             h = blk.forward(h, t, tape['b'], tape['l'], training)
         logits = self.head_forward(h, tape)
-        self.tape = tape if keep_tape else None
-        return logits
+        return logits, (tape if keep_tape else None)
 
     def head_backward(self, dlogits, tape, next_scale=None):
         m, sink = self.model, self.sink
@@ -251,10 +249,9 @@ class ViTRT:
         ops.colsum(dpatch, bbuf, accumulate=bacc)
         sink.done(bias, bbuf)
 
-    def backward(self, dlogits):
-        tape, sink = self.tape, self.sink
+    def backward(self, dlogits, tape):
+        sink = self.sink
         assert tape is not None, 'backward called without a training forward'
-        self.tape = None
         tapes = tape['blocks']
         dx, dxb = self.head_backward(dlogits, tape, next_scale=tapes[-1]['s2'] if tapes else None)
         for i in range(len(self.blocks) - 1, -1, -1):

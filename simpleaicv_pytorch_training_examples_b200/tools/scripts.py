@@ -9,16 +9,7 @@ small all-reduce and ONE device->host read per step; there is no per-step barrie
 import torch
 import torch.distributed as dist
 
-
-class AverageMeter:
-    def __init__(self):
-        self.val = self.avg = self.sum = self.count = 0
-
-    def update(self, val, n=1):
-        self.val = val
-        self.sum += val * n
-        self.count += n
-        self.avg = self.sum / self.count
+from ..classification.common import AccMeter, AverageMeter
 
 
 def _world():
@@ -99,7 +90,7 @@ def test_classification(test_loader, model, criterion, config):
     (tools/scripts.py:74-95) so index ties resolve identically."""
     model.eval()
     group = getattr(config, 'group', None)
-    correct1 = correct5 = seen = 0.
+    meter = AccMeter()
     loss_sum = 0.
     for data in test_loader:
         images, labels = data['image'].cuda(non_blocking=True), data['label'].cuda(non_blocking=True)
@@ -108,10 +99,9 @@ def test_classification(test_loader, model, criterion, config):
         _, pred = torch.topk(outputs.float(), k=5, dim=1, largest=True, sorted=True)
         pred = pred.t()
         hit = pred.eq(labels.view(1, -1).expand_as(pred))
-        correct1 += hit[:1].reshape(-1).float().sum().item()
-        correct5 += hit[:5].reshape(-1).float().sum().item()
-        seen += images.size(0)
+        meter.update(hit[:1].reshape(-1).float().sum().item(), hit[:5].reshape(-1).float().sum().item(), images.size(0))
         loss_sum += loss.item() * images.size(0)
-    correct1, correct5, seen, loss_sum = all_reduce_operation_in_group_for_variables(
-        [correct1, correct5, seen, loss_sum], dist.ReduceOp.SUM, group)
-    return correct1 / seen * 100, correct5 / seen * 100, loss_sum / seen
+    meter.acc1_correct_num, meter.acc5_correct_num, meter.sample_num, loss_sum = all_reduce_operation_in_group_for_variables(
+        [meter.acc1_correct_num, meter.acc5_correct_num, meter.sample_num, loss_sum], dist.ReduceOp.SUM, group)
+    meter.compute()
+    return meter.acc1 * 100, meter.acc5 * 100, loss_sum / meter.sample_num

@@ -16,7 +16,8 @@ import torch.distributed as dist
 from torch.utils.data import DataLoader
 
 from .scripts import test_classification, train_classification
-from .utils import Scheduler, build_optimizer, build_training_mode, get_logger, set_seed
+from .utils import (Scheduler, build_optimizer, build_training_mode, checkpoint_model_state, get_logger, load_model_state,
+                    set_seed, unwrap)
 
 
 def parse_args():
@@ -73,15 +74,15 @@ def main():
             if not k.startswith('__') and k not in ('model',):
                 logger.info(f'{k}: {v}')
 
-    start_epoch, best_acc1 = 1, 0.
+    start_epoch, best_acc1, train_time = 1, 0., 0.
     if os.path.exists(resume_model):
         ckpt = torch.load(resume_model, map_location='cpu', weights_only=True)
-        model.load_state_dict(ckpt['model_state_dict'])
+        load_model_state(model, ckpt['model_state_dict'])
         optimizer.load_state_dict(ckpt['optimizer_state_dict'])
         scheduler.load_state_dict(ckpt['scheduler_state_dict'])
         if config.ema_model is not None and 'ema_model_state_dict' in ckpt:
             config.ema_model.ema_model.load_state_dict(ckpt['ema_model_state_dict'])
-        start_epoch, best_acc1 = ckpt['epoch'] + 1, ckpt['best_acc1']
+        start_epoch, best_acc1, train_time = ckpt['epoch'] + 1, ckpt['best_acc1'], ckpt.get('time', 0.)
         logger.info(f'resumed from epoch {ckpt["epoch"]:0>3d}, best_acc1 {best_acc1:.3f}%') if master else None
 
     for epoch in range(start_epoch, config.epochs + 1):
@@ -91,14 +92,15 @@ def main():
         train_loss = train_classification(train_loader, model, train_criterion, optimizer, scheduler, epoch, logger, config)
         eval_model = config.ema_model.ema_model if config.ema_model is not None else model
         acc1, acc5, test_loss = test_classification(test_loader, eval_model, test_criterion, config)
+        train_time += (time.time() - t0) / 3600
         if master:
             logger.info(f'epoch {epoch:0>3d}: train loss {train_loss:.4f}, acc1 {acc1:.3f}%, acc5 {acc5:.3f}%, '
                         f'test loss {test_loss:.4f}, {(time.time() - t0) / 3600:.3f} h')
-            if acc1 > best_acc1:
+            if best_acc1 < acc1 <= 100:
                 best_acc1 = acc1
-                torch.save(eval_model.state_dict(), os.path.join(checkpoint_dir, 'best.pth'))
-            state = {'epoch': epoch, 'time': (time.time() - t0) / 3600, 'best_acc1': best_acc1, 'test_loss': test_loss,
-                     'lr': scheduler.current_lr, 'model_state_dict': model.state_dict(),
+                torch.save(unwrap(eval_model).state_dict(), os.path.join(checkpoint_dir, 'best.pth'))   # no 'module.' prefix
+            state = {'epoch': epoch, 'time': train_time, 'best_acc1': best_acc1, 'test_loss': test_loss,
+                     'lr': scheduler.current_lr, 'model_state_dict': checkpoint_model_state(model),   # 'module.'-prefixed
                      'optimizer_state_dict': optimizer.state_dict(), 'scheduler_state_dict': scheduler.state_dict()}
             if config.ema_model is not None:
                 state['ema_model_state_dict'] = config.ema_model.ema_model.state_dict()

@@ -215,6 +215,28 @@ class CudaPrefetcher:
             yield cur
 
 
+def unwrap(model):
+    """The bare network under a data-parallel wrapper (torch DDP or B200DataParallel)."""
+    return model.module if hasattr(model, 'module') else model
+
+
+def checkpoint_model_state(model):
+    """``model_state_dict`` of latest.pth in the REFERENCE's layout: the reference always saves the
+    state_dict of the DDP-wrapped model (tools/train_classification_model.py:226-229), i.e. every key
+    carries the ``module.`` prefix, whatever the world size.  best.pth holds ``unwrap(model).state_dict()``
+    (no prefix, :213-221)."""
+    return {'module.' + k: v for k, v in unwrap(model).state_dict().items()}
+
+
+def load_model_state(model, state_dict, strict=True):
+    """Loads a ``model_state_dict`` written by this package or by the reference, with or without the
+    ``module.`` prefix, into a wrapped or unwrapped model (so runs can resume across 1 <-> N GPUs and
+    from reference checkpoints)."""
+    if state_dict and all(k.startswith('module.') for k in state_dict):
+        state_dict = {k[len('module.'):]: v for k, v in state_dict.items()}
+    return unwrap(model).load_state_dict(state_dict, strict=strict)
+
+
 def build_training_mode(config, model):
     """Returns (model, ema_model, scaler).  The reference wraps in torch DDP and creates a
     GradScaler; here the wrapper is distributed.B200DataParallel (bucketed NCCL all-reduce fed

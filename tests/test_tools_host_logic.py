@@ -56,15 +56,43 @@ def test_scheduler_closed_forms(name, params):
         assert abs(opt.param_groups[0]['lr'] - exp) < 1e-12 and abs(s.current_lr - exp) < 1e-12
 
 
-@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'tools')), reason='reference checkout not present')
+def _ref_utils():
+    from baseline import ref_import
+    if not ref_import.available():
+        pytest.skip('reference not installed (baseline/install_ref.sh)')
+    return ref_import.module('tools.utils')
+
+
+def _canon(o):
+    return sorted((g['weight_decay'], round(g['lr'], 15), sorted(id(p) for p in g['params'])) for g in o.param_groups)
+
+
+def test_vit_layer_decay_groups_match_reference_utils():
+    """ViT layer-wise lr decay + no-weight-decay name list (tools/utils.py:313-420), the AdamW setting of
+    00.classification_training/imagenet/vit_base_patch16_*/train_config.py."""
+    ref_utils = _ref_utils()
+    m = backbones.vit_base_patch16(image_size=32, num_classes=10)
+
+    class C:
+        optimizer = ('AdamW', {'lr': 5e-4, 'global_weight_decay': False, 'weight_decay': 0.05,
+                               'no_weight_decay_layer_name_list': ['position_encoding', 'cls_token'],
+                               'lr_layer_decay': 0.65, 'lr_layer_decay_block': m.blocks, 'block_name': 'blocks'})
+        scheduler = ('CosineLR', {'warm_up_epochs': 5, 'min_lr': 1e-6})
+        epochs = 100
+    ro, _ = ref_utils.build_optimizer(C, m)
+    mo, _ = my_utils.build_optimizer(C, m)
+    assert _canon(ro) == _canon(mo)
+    assert type(ro) is type(mo) and ro.defaults['betas'] == mo.defaults['betas'] and ro.defaults['eps'] == mo.defaults['eps']
+    rs, ms = ref_utils.Scheduler(C, ro), my_utils.Scheduler(C, mo)
+    for e in [0.0, 2.5, 5.0, 50.0, 99.5]:
+        rs.step(ro, e)
+        ms.step(mo, e)
+        assert abs(rs.current_lr - ms.current_lr) < 1e-15
+        assert _canon(ro) == _canon(mo)
+
+
 def test_groups_and_schedule_match_reference_utils():
-    if 'calflops' not in sys.modules:
-        stub = types.ModuleType('calflops')
-        stub.calculate_flops = lambda *a, **k: None
-        sys.modules['calflops'] = stub
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    from tools import utils as ref_utils
+    ref_utils = _ref_utils()
     m = backbones.resnet50cifar(num_classes=10)
     ro, _ = ref_utils.build_optimizer(_Cfg, m)
     mo, _ = my_utils.build_optimizer(_Cfg, m)
@@ -79,3 +107,61 @@ def test_groups_and_schedule_match_reference_utils():
         ms.step(mo, e)
         assert abs(rs.current_lr - ms.current_lr) < 1e-12
         assert sorted(g['lr'] for g in ro.param_groups) == sorted(g['lr'] for g in mo.param_groups)
+
+
+def test_checkpoint_key_layout_matches_reference_and_round_trips():
+    """latest.pth keeps the reference's DDP key layout ('module.' prefix) at every world size, best.pth has
+    none (reference tools/train_classification_model.py:213-229); loading accepts both layouts into wrapped
+    and unwrapped models."""
+    import torch
+    import torch.nn as nn
+    from simpleaicv_pytorch_training_examples_b200.tools import utils
+
+    class Wrapper(nn.Module):   # stands in for DistributedDataParallel / B200DataParallel
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+
+    def net(seed):
+        torch.manual_seed(seed)
+        return nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4))
+
+    src = net(0)
+    ref_latest = Wrapper(src).state_dict()                      # what the reference writes
+    assert all(k.startswith('module.') for k in ref_latest)
+    assert list(utils.checkpoint_model_state(src).keys()) == list(ref_latest.keys())            # unwrapped, world 1
+    assert list(utils.checkpoint_model_state(Wrapper(src)).keys()) == list(ref_latest.keys())   # wrapped, world N
+    for target in (net(1), Wrapper(net(2))):
+        utils.load_model_state(target, ref_latest)               # reference latest.pth
+        assert all(torch.equal(a, b) for a, b in zip(utils.unwrap(target).state_dict().values(), src.state_dict().values()))
+    for target in (net(3), Wrapper(net(4))):
+        utils.load_model_state(target, src.state_dict())         # reference best.pth (no prefix)
+        assert all(torch.equal(a, b) for a, b in zip(utils.unwrap(target).state_dict().values(), src.state_dict().values()))
+
+
+def test_meters_and_amp_type_match_reference():
+    """AverageMeter / AccMeter behave like the reference's (classification/common.py:668-709); get_amp_type
+    returns bf16 for CPU-resident models (no device to inspect) and has 'B200' in its whitelist."""
+    import inspect
+    import torch
+    from baseline import ref_import
+    from simpleaicv_pytorch_training_examples_b200.classification import common
+    if ref_import.available():
+        rc = ref_import.module('SimpleAICV.classification.common')
+        pairs = [(common.AverageMeter(), rc.AverageMeter()), (common.AccMeter(), rc.AccMeter())]
+    else:
+        pairs = [(common.AverageMeter(), None), (common.AccMeter(), None)]
+    a, ra = pairs[0]
+    for v, n in [(1.5, 4), (0.25, 2), (3.0, 1)]:
+        a.update(v, n)
+        ra.update(v, n) if ra is not None else None
+    assert abs(a.avg - (1.5 * 4 + 0.5 + 3.0) / 7) < 1e-12 and (ra is None or (a.avg, a.sum, a.count, a.val) == (ra.avg, ra.sum, ra.count, ra.val))
+    m, rm = pairs[1]
+    for c1, c5, n in [(3, 7, 10), (5, 9, 10)]:
+        m.update(c1, c5, n)
+        rm.update(c1, c5, n) if rm is not None else None
+    m.compute()
+    rm.compute() if rm is not None else None
+    assert (m.acc1, m.acc5) == (0.4, 0.8) and (rm is None or (m.acc1, m.acc5) == (rm.acc1, rm.acc5))
+    assert "'B200'" in inspect.getsource(common.get_amp_type)
+    assert common.get_amp_type(torch.nn.Linear(2, 2)) == torch.bfloat16
