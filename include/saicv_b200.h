@@ -24,6 +24,8 @@ extern "C" {
 #define SAICV_EPI_GELU 4
 #define SAICV_EPI_DIRECT 8 /* debugging: registers -> global without the TMA store path */
 #define SAICV_EPI_RESID 16 /* += fp32 residual[M, N] */
+#define SAICV_EPI_ADD_BF16 32   /* saicv_linear_dgrad: the aux bf16 operand is ADDED to dx */
+#define SAICV_EPI_MUL_DRELU 512 /* saicv_linear_dgrad: the aux bf16 operand is a ReLU output; dx *= (aux > 0) */
 
 int saicv_version(void);
 const char* saicv_last_error(void);
@@ -44,7 +46,9 @@ int saicv_linear_fwd(const void* x, const void* w, const float* bias, const floa
  * floats, <= SAICV_BN_PARTIAL_ROWS rows) and hand it to saicv_bn_finalize with that row count. */
 int saicv_gemm_stats_rows(long long out_rows, int out_cols);
 /* dx[M,K] = (dy[M,N] w[N,K]) (* gelu'(gelu_pre[M,K])) (+ resid[M,K]); dy,w,gelu_pre bf16; dx bf16
- * or fp32; gelu_pre (the pre-activation saved by the forward, vit.py:87-89) and resid may be NULL. */
+ * or fp32; gelu_pre (the pre-activation saved by the forward, vit.py:87-89) and resid may be NULL.
+ * With SAICV_EPI_MUL_DRELU / SAICV_EPI_ADD_BF16 in flags the bf16 operand passed as gelu_pre is instead a
+ * ReLU output used as a mask (van.py:46-51: fc2 <- relu) / a second bf16 gradient added to dx. */
 int saicv_linear_dgrad(const void* dy, const void* w, const float* resid, const void* gelu_pre,
                        void* dx, int M, int N, int K, int flags, int out_f32, void* stream);
 /* dw_partial[splits][N][K] (fp32) = dy[M,N]^T x[M,K], reduction over M split `splits` ways.
@@ -186,13 +190,97 @@ int saicv_token_pool_fwd(const float* x, float* pooled, int b, int l, int c, int
                          void* stream);
 int saicv_token_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, const float* bf16_row_scale,
                          int b, int l, int c, int mean_pool, void* stream);
-/* MultiHeadAttention core (vit.py:66-76): qkv bf16 [b][l][3][h][d] -> out bf16 [b][l][h*d] =
- * softmax(q k^T * scale) v, fused (the l x l matrix is never written); lse[b][h][l] (log2 domain)
- * is kept for the backward.  d == 64, l <= 256. */
+/* ---- VAN (SimpleAICV/classification/backbones/van.py) ------------------------------------------------
+ * Depthwise convolution k x k (3, 5, 7), dilation dil, 'same' padding dil*(k-1)/2, stride 1, NHWC bf16
+ * (van.py:20-35 DWConv 3x3; :63-77 LKA 5x5 and 7x7 dilation 3).  w: fp32 [C][1][k][k] (torch layout),
+ * bias fp32 [C] or NULL; relu: fused ReLU (van.py:49-50); flip: mirrored taps = the data gradient. */
+int saicv_dwconv_fwd(const void* x, const float* w, const float* bias, void* y, int n, int h, int wd,
+                     int c, int k, int dil, int relu, int flip, void* stream);
+/* dw[C][1][k][k] (+)= sum over pixels dy * shifted x; partial: fp32 workspace
+ * [saicv_dwconv_wgrad_blocks(n*h*w)][k*k][C]; fixed-order two-stage reduction. */
+int saicv_dwconv_wgrad_blocks(long long npix);
+int saicv_dwconv_wgrad(const void* dy, const void* x, float* partial, float* dw, int n, int h, int wd,
+                       int c, int k, int dil, int accumulate, void* stream);
+/* out = a * b (LKA gate u * attn, van.py:91, and its gradient w.r.t. attn); bf16, n % 8 == 0. */
+int saicv_mul_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+/* out = (dg * c1 + dlk) * (p1 > 0): gradient at the input of the ReLU that produced p1 (van.py:106-108),
+ * from the gate (dg * c1) and from the LKA convolutions (dlk). */
+int saicv_gate_bwd(const void* dg, const void* c1, const void* dlk, const void* p1, void* out,
+                   long long n, void* stream);
+/* Residual update with layer scale (van.py:183-184): out(fp32) = x + row_scale[row/rows_per_scale] *
+ * ls[c] * (branch [+ shortcut]); x bf16 or fp32 (x_f32), branch / shortcut bf16 [rows][c], shortcut and
+ * row_scale (drop path, van.py:118-151) may be NULL. */
+int saicv_ls_residual_fwd(const void* x, int x_f32, const void* branch, const void* shortcut,
+                          const float* ls, const float* row_scale, int rows_per_scale, float* out,
+                          long long rows, int c, void* stream);
+/* dy(bf16) = row_scale * ls[c] * dxn; dls[c] (+)= sum_rows row_scale * dxn * (branch [+ shortcut]);
+ * partial: fp32 workspace [SAICV_BN_PARTIAL_ROWS][c]. */
+int saicv_ls_residual_bwd(const float* dxn, const void* branch, const void* shortcut, const float* ls,
+                          const float* row_scale, int rows_per_scale, void* dy, float* partial,
+                          float* dls, long long rows, int c, int accumulate, void* stream);
+/* Train-mode BatchNorm2d over [rows][c] with bf16 OR fp32 input / output (van.py:160-165,205-207: BN of the
+ * fp32 residual stream feeding bf16 GEMMs; :200-207 BN of the bf16 patch-embedding conv into the stream).
+ * stats: partial sums [saicv_bn_generic_partial_rows(rows, c)][2][c] for saicv_bn_finalize; apply:
+ * out = x*scale + shift; bwd: dx = BN'(g) [+ dres fp32], dgamma/dbeta (+)=; partial [..][2][c], sums [2][c]. */
+int saicv_bn_generic_partial_rows(long long rows, int c);
+int saicv_bn_stats_generic(const void* x, int x_f32, float* partial, long long rows, int c, void* stream);
+int saicv_bn_apply_generic(const void* x, int x_f32, const float* scale_shift, void* out, int out_f32,
+                           long long rows, int c, void* stream);
+int saicv_bn_bwd_generic(const void* x, int x_f32, const void* g, int g_f32, const float* saved,
+                         const float* gamma, const float* dres, float* partial, float* sums, void* dx,
+                         int dx_f32, float* dgamma, float* dbeta, long long rows, int c, int accumulate,
+                         void* stream);
+/* NHWC bf16 im2col / col2im for the strided patch-embedding convolutions whose channel counts are not
+ * multiples of 64 (van.py:189-208: 3x3 stride 2): cols[(n,p,q)][(r*k+s)*c + ch]. */
+int saicv_im2col_nhwc(const void* x, void* cols, int n, int h, int w, int c, int k, int stride, int pad,
+                      void* stream);
+int saicv_col2im_nhwc(const void* dcols, void* dx, int n, int h, int w, int c, int k, int stride, int pad,
+                      void* stream);
+
+/* ---- fused multi-head attention on tcgen05 / TMEM (csrc/attn_sm100.cuh) ------------------------------
+ * Replaces the materialised attention of the reference: vit.py:62-80 (q k^T * scale, softmax, @ v),
+ * segment_anything/image_encoder.py:167-184 (+ decomposed rel-pos bias, folded into extra score columns by
+ * the caller: dqk = head_dim + bias columns), detection/models/detr.py:54-56,103-109 (nn.MultiheadAttention
+ * with key_padding_mask, self- and cross-attention).
+ *   S = Q K^T * scale  [lq x lk]; masked keys -> -inf; P = softmax(S); out = P V; the l x l matrices never
+ *   touch HBM.  q, k: bf16 rows of dqk elements; v, out: bf16 rows of dv elements; every tensor is addressed
+ *   as [b][h][row] through element strides {batch, head, row} (rows contiguous, 16-byte aligned), so packed
+ *   qkv [b][l][3][h][d], [b*h][l][d] and [b][l][h*d] layouts are all views.  lse [b][h][lq] fp32 holds
+ *   log2(sum exp2(s*scale*log2e)) for the backward.  key_mask_bits: [b][mask_words] uint32, bit k%32 of
+ *   word k/32 set = key k is padding (NULL: none); mask_words*32 >= lk rounded up to 128.
+ *   Supported (dqk, dv): (32,32) (64,64) (80,80) (96,64) (112,80) (192,64) (208,80). */
+typedef struct {
+  const void* q; const void* k; const void* v;
+  void* out;
+  float* lse;
+  long long q_strides[3], k_strides[3], v_strides[3], o_strides[3];
+  const unsigned int* key_mask_bits;
+  int mask_words;
+  int b, h, lq, lk, dqk, dv;
+  float scale;
+} saicv_attn_args;
+int saicv_attn_fwd(const saicv_attn_args* a, void* stream);
+/* Backward: fwd holds the forward's arguments (out = the forward output, lse as written by it); dout has the
+ * layout of out.  delta: fp32 workspace [b][h][lq] (rowsum(dout * out), written here).  dq rows have dqk
+ * columns; dk rows get their leading dk_cols columns (0 = all dqk; the bias columns of k carry no gradient);
+ * dv rows dv columns.  Two deterministic phases (no atomics): dQ per query tile, dK/dV per key tile. */
+typedef struct {
+  saicv_attn_args fwd;
+  const void* dout;
+  float* delta;
+  void* dq; void* dk; void* dv;
+  long long dq_strides[3], dk_strides[3], dv_strides[3];
+  int dk_cols;
+} saicv_attn_bwd_args;
+int saicv_attn_bwd(const saicv_attn_bwd_args* a, void* stream);
+/* 1 if an attention kernel found its shared-memory window misaligned (synchronises; for tests). */
+int saicv_attn_error(void);
+/* ViT convenience entries (vit.py:66-76): qkv bf16 [b][l][3][h][d] -> out bf16 [b][l][h*d]; lse [b][h][l];
+ * backward writes dqkv in the layout of qkv; delta: fp32 workspace [b][h][l]. */
 int saicv_attention_fwd(const void* qkv, void* out, float* lse, int b, int l, int h, int d,
                         float scale, void* stream);
 int saicv_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
-                        void* dqkv, int b, int l, int h, int d, float scale, void* stream);
+                        float* delta, void* dqkv, int b, int l, int h, int d, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,22 @@ class ConvShape(ctypes.Structure):
                 ('pad', c_int)]
 
 
+class AttnArgs(ctypes.Structure):
+    """saicv_attn_args (include/saicv_b200.h)."""
+    _fields_ = [('q', c_void_p), ('k', c_void_p), ('v', c_void_p), ('out', c_void_p), ('lse', c_void_p),
+                ('q_strides', c_ll * 3), ('k_strides', c_ll * 3), ('v_strides', c_ll * 3), ('o_strides', c_ll * 3),
+                ('key_mask_bits', c_void_p), ('mask_words', c_int),
+                ('b', c_int), ('h', c_int), ('lq', c_int), ('lk', c_int), ('dqk', c_int), ('dv', c_int),
+                ('scale', c_float)]
+
+
+class AttnBwdArgs(ctypes.Structure):
+    """saicv_attn_bwd_args (include/saicv_b200.h)."""
+    _fields_ = [('fwd', AttnArgs), ('dout', c_void_p), ('delta', c_void_p),
+                ('dq', c_void_p), ('dk', c_void_p), ('dv', c_void_p),
+                ('dq_strides', c_ll * 3), ('dk_strides', c_ll * 3), ('dv_strides', c_ll * 3), ('dk_cols', c_int)]
+
+
 # name -> argtypes; every symbol declared in include/saicv_b200.h is listed here and
 # tests/test_capi_symbols.py checks the header, this table and the .so agree.
 SIGNATURES = {
@@ -66,7 +82,23 @@ SIGNATURES = {
     'saicv_token_pool_fwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     'saicv_token_pool_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     'saicv_attention_fwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
-    'saicv_attention_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    'saicv_attention_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    'saicv_attn_fwd': [ctypes.POINTER(AttnArgs), c_void_p],
+    'saicv_attn_bwd': [ctypes.POINTER(AttnBwdArgs), c_void_p],
+    'saicv_attn_error': [],
+    'saicv_dwconv_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_dwconv_wgrad_blocks': [c_ll],
+    'saicv_dwconv_wgrad': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_mul_bf16': [c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
+    'saicv_gate_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
+    'saicv_ls_residual_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_int, c_void_p],
+    'saicv_ls_residual_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p],
+    'saicv_bn_generic_partial_rows': [c_ll, c_int],
+    'saicv_bn_stats_generic': [c_void_p, c_int, c_void_p, c_ll, c_int, c_void_p],
+    'saicv_bn_apply_generic': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p],
+    'saicv_bn_bwd_generic': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p],
+    'saicv_im2col_nhwc': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_col2im_nhwc': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
 }
 
 _lib = None

@@ -1,0 +1,278 @@
+// Host side of the tcgen05 attention family (attn_sm100.cuh): tensor maps, template dispatch, launches.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "../../include/saicv_b200.h"
+#include "attn_sm100.cuh"
+#include "host_util.h"
+
+using namespace saicv;
+
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+int g_sms = 0;
+std::once_flag g_once;
+bool g_ok = false;
+__device__ int g_attn_error = 0;
+
+void init() {
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    return;
+  }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    set_error("cudaGetDeviceProperties failed");
+    return;
+  }
+  if (prop.major != 10) {
+    set_error("libsaicv_b200 requires an sm_100 (B200) device, found sm_%d%d", prop.major, prop.minor);
+    return;
+  }
+  g_sms = prop.multiProcessorCount;
+  g_ok = true;
+}
+bool ensure() {
+  std::call_once(g_once, init);
+  return g_ok;
+}
+
+// [B][H][L][D] view with arbitrary (16-byte aligned) strides; box = 64 columns x `rows` rows, 128B swizzle,
+// out-of-range rows / columns read as zero.
+bool encode_4d(CUtensorMap* m, const void* ptr, int D, int L, int H, int B, const long long* strides /*b,h,row*/,
+               uint32_t rows) {
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)L, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t st[3] = {(cuuint64_t)strides[2] * 2, (cuuint64_t)strides[1] * 2, (cuuint64_t)strides[0] * 2};
+  cuuint32_t box[4] = {64, rows, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (st[0] & 15) || (st[1] & 15) || (st[2] & 15)) {
+    set_error("attention operand not 16-byte aligned (ptr %p strides %lld %lld %lld elements)", ptr, strides[0], strides[1], strides[2]);
+    return false;
+  }
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, st, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(attention 4d) failed: %d (D=%d L=%d H=%d B=%d strides %lld %lld %lld)", (int)r, D, L, H, B,
+              strides[0], strides[1], strides[2]);
+    return false;
+  }
+  return true;
+}
+
+template <typename K>
+int persistent_grid(K kernel, int smem, long long total) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kAttnThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+  if (occ > 2) occ = 2;
+  const long long g = (long long)g_sms * occ;
+  return (int)(total < g ? total : g);
+}
+
+template <int DQK, int DV, int MINB>
+int launch_fwd(const saicv_attn_args* a, cudaStream_t st) {
+  using Cfg = AttnFwdCfg<DQK, DV, MINB>;
+  auto kernel = attn_fwd_sm100_kernel<DQK, DV, MINB>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return set_error("attention fwd<%d,%d>: smem %d: %s", DQK, DV, Cfg::kSmemBytes, cudaGetErrorString(e));
+    }
+    attr = true;
+  }
+  CUtensorMap tq, tk, tv;
+  if (!encode_4d(&tq, a->q, DQK, a->lq, a->h, a->b, a->q_strides, 128)) return 2;
+  if (!encode_4d(&tk, a->k, DQK, a->lk, a->h, a->b, a->k_strides, 128)) return 2;
+  if (!encode_4d(&tv, a->v, DV, a->lk, a->h, a->b, a->v_strides, 128)) return 2;
+  AttnParams p{};
+  p.B = a->b; p.H = a->h; p.Lq = a->lq; p.Lk = a->lk;
+  p.num_q_tiles = (a->lq + 127) / 128;
+  p.scale = a->scale;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.o_sb = a->o_strides[0]; p.o_sh = a->o_strides[1]; p.o_sl = a->o_strides[2];
+  p.lse = a->lse;
+  p.mask_bits = a->key_mask_bits; p.mask_words = a->mask_words;
+  void* flag = nullptr;
+  cudaGetSymbolAddress(&flag, g_attn_error);
+  p.error_flag = reinterpret_cast<int*>(flag);
+  const long long total = (long long)a->b * a->h * p.num_q_tiles;
+  const int grid = persistent_grid(kernel, Cfg::kSmemBytes, total);
+  kernel<<<grid, kAttnThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, p);
+  return check_launch("attn_fwd_sm100_kernel");
+}
+
+template <int DQK, int DV, bool KEYS, int TCOLS, int MINB>
+int launch_bwd_phase(const saicv_attn_bwd_args* a, cudaStream_t st) {
+  using Cfg = AttnBwdCfg<DQK, DV, KEYS, TCOLS, MINB>;
+  auto kernel = attn_bwd_sm100_kernel<DQK, DV, KEYS, TCOLS, MINB>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return set_error("attention bwd<%d,%d,%d>: smem %d: %s", DQK, DV, (int)KEYS, Cfg::kSmemBytes, cudaGetErrorString(e));
+    }
+    attr = true;
+  }
+  const saicv_attn_args* f = &a->fwd;
+  CUtensorMap r0, r1, c0, c1;
+  if (!KEYS) {
+    if (!encode_4d(&r0, f->q, DQK, f->lq, f->h, f->b, f->q_strides, 128)) return 2;
+    if (!encode_4d(&r1, a->dout, DV, f->lq, f->h, f->b, f->o_strides, 128)) return 2;
+    if (!encode_4d(&c0, f->k, DQK, f->lk, f->h, f->b, f->k_strides, 64)) return 2;
+    if (!encode_4d(&c1, f->v, DV, f->lk, f->h, f->b, f->v_strides, 64)) return 2;
+  } else {
+    if (!encode_4d(&r0, f->k, DQK, f->lk, f->h, f->b, f->k_strides, 128)) return 2;
+    if (!encode_4d(&r1, f->v, DV, f->lk, f->h, f->b, f->v_strides, 128)) return 2;
+    if (!encode_4d(&c0, f->q, DQK, f->lq, f->h, f->b, f->q_strides, 64)) return 2;
+    if (!encode_4d(&c1, a->dout, DV, f->lq, f->h, f->b, f->o_strides, 64)) return 2;
+  }
+  AttnBwdParams p{};
+  p.B = f->b; p.H = f->h; p.Lq = f->lq; p.Lk = f->lk;
+  p.num_tiles = ((KEYS ? f->lk : f->lq) + 127) / 128;
+  p.scale = f->scale;
+  p.scale_log2 = f->scale * 1.4426950408889634f;
+  p.lse = f->lse; p.delta = a->delta;
+  p.mask_bits = f->key_mask_bits; p.mask_words = f->mask_words;
+  if (!KEYS) {
+    p.d_out0 = reinterpret_cast<__nv_bfloat16*>(a->dq);
+    p.s0b = a->dq_strides[0]; p.s0h = a->dq_strides[1]; p.s0l = a->dq_strides[2];
+  } else {
+    p.d_out0 = reinterpret_cast<__nv_bfloat16*>(a->dk);
+    p.s0b = a->dk_strides[0]; p.s0h = a->dk_strides[1]; p.s0l = a->dk_strides[2];
+    p.d_out1 = reinterpret_cast<__nv_bfloat16*>(a->dv);
+    p.s1b = a->dv_strides[0]; p.s1h = a->dv_strides[1]; p.s1l = a->dv_strides[2];
+  }
+  p.dk_cols = a->dk_cols > 0 ? a->dk_cols : DQK;
+  void* flag = nullptr;
+  cudaGetSymbolAddress(&flag, g_attn_error);
+  p.error_flag = reinterpret_cast<int*>(flag);
+  const long long total = (long long)f->b * f->h * p.num_tiles;
+  const int grid = persistent_grid(kernel, Cfg::kSmemBytes, total);
+  kernel<<<grid, kAttnThreads, Cfg::kSmemBytes, st>>>(r0, r1, c0, c1, p);
+  return check_launch("attn_bwd_sm100_kernel");
+}
+
+// delta[b][h][q] = sum_d dO * O   (one warp per row)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
+                                  int B, int H, int L, int DV, long long sb, long long sh, long long sl) {
+  const long long rows = (long long)B * H * L;
+  const int lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
+       r += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int q = (int)(r % L);
+    const long long bh = r / L;
+    const int h = (int)(bh % H);
+    const long long b = bh / H;
+    const long long off = b * sb + h * sh + q * sl;
+    float s = 0.f;
+    for (int i = lane * 2; i < DV; i += 64) {
+      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off + i));
+      const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d_o + off + i));
+      s += x.x * y.x + x.y * y.y;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) delta[r] = s;
+  }
+}
+
+template <int DQK, int DV>
+int fwd_for(const saicv_attn_args* a, cudaStream_t st) {
+  // two CTAs per SM whenever the tiles of both fit (hd <= 64 without bias columns)
+  constexpr bool two = AttnFwdCfg<DQK, DV, 2>::kSmemBytes <= 115712;
+  return launch_fwd<DQK, DV, two ? 2 : 1>(a, st);
+}
+template <int DQK, int DV>
+int bwd_for(const saicv_attn_bwd_args* a, cudaStream_t st) {
+  constexpr int colsA = 128 + ((DQK + 31) & ~31), colsB = 128 + ((DV + 31) & ~31) + ((DQK + 31) & ~31);
+  constexpr int tA = colsA <= 256 ? 256 : 512, tB = colsB <= 256 ? 256 : 512;
+  constexpr bool twoA = tA == 256 && AttnBwdCfg<DQK, DV, false, tA, 2>::kSmemBytes <= 115712;
+  constexpr bool twoB = tB == 256 && AttnBwdCfg<DQK, DV, true, tB, 2>::kSmemBytes <= 115712;
+  if (int e = launch_bwd_phase<DQK, DV, false, tA, twoA ? 2 : 1>(a, st)) return e;
+  return launch_bwd_phase<DQK, DV, true, tB, twoB ? 2 : 1>(a, st);
+}
+
+#define SAICV_ATTN_SHAPES(X) X(32, 32) X(64, 64) X(80, 80) X(96, 64) X(112, 80) X(192, 64) X(208, 80)
+
+}  // namespace
+
+extern "C" {
+
+int saicv_attn_error(void) {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, g_attn_error, sizeof(int));
+  return v;
+}
+
+int saicv_attn_fwd(const saicv_attn_args* a, void* stream) {
+  if (!ensure()) return 1;
+  if (a->lq < 1 || a->lk < 1 || a->b < 1 || a->h < 1) return set_error("saicv_attn_fwd: empty problem");
+  if (a->key_mask_bits && a->mask_words * 32 < ((a->lk + 127) / 128) * 128)
+    return set_error("saicv_attn_fwd: mask_words must cover lk rounded up to 128 keys");
+#define X(Q, V) if (a->dqk == Q && a->dv == V) return fwd_for<Q, V>(a, (cudaStream_t)stream);
+  SAICV_ATTN_SHAPES(X)
+#undef X
+  return set_error("saicv_attn_fwd: unsupported (score width, value width) = (%d, %d)", a->dqk, a->dv);
+}
+
+int saicv_attn_bwd(const saicv_attn_bwd_args* a, void* stream) {
+  if (!ensure()) return 1;
+  const saicv_attn_args* f = &a->fwd;
+  if (a->dk_cols < 0 || a->dk_cols > f->dqk || (a->dk_cols % 16)) return set_error("saicv_attn_bwd: bad dk_cols %d", a->dk_cols);
+  {
+    const long long rows = (long long)f->b * f->h * f->lq;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    attn_delta_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(f->out), reinterpret_cast<const __nv_bfloat16*>(a->dout), a->delta, f->b, f->h,
+        f->lq, f->dv, f->o_strides[0], f->o_strides[1], f->o_strides[2]);
+    if (int e = check_launch("attn_delta_kernel")) return e;
+  }
+#define X(Q, V) if (f->dqk == Q && f->dv == V) return bwd_for<Q, V>(a, (cudaStream_t)stream);
+  SAICV_ATTN_SHAPES(X)
+#undef X
+  return set_error("saicv_attn_bwd: unsupported (score width, value width) = (%d, %d)", f->dqk, f->dv);
+}
+
+// ---- packed-qkv convenience entries used by the ViT runtime: qkv [B, L, 3, H, d], out [B, L, H*d]
+static void fill_packed(saicv_attn_args* a, const void* qkv, void* out, float* lse, int b, int l, int h, int d, float scale) {
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  const long long sl = 3LL * h * d, sb = (long long)l * sl;
+  a->q = base; a->k = base + (long long)h * d; a->v = base + 2LL * h * d;
+  a->out = out; a->lse = lse;
+  for (auto* s : {a->q_strides, a->k_strides, a->v_strides}) { s[0] = sb; s[1] = d; s[2] = sl; }
+  a->o_strides[0] = (long long)l * h * d; a->o_strides[1] = d; a->o_strides[2] = (long long)h * d;
+  a->key_mask_bits = nullptr; a->mask_words = 0;
+  a->b = b; a->h = h; a->lq = l; a->lk = l; a->dqk = d; a->dv = d; a->scale = scale;
+}
+
+int saicv_attention_fwd(const void* qkv, void* out, float* lse, int b, int l, int h, int d, float scale, void* stream) {
+  saicv_attn_args a{};
+  fill_packed(&a, qkv, out, lse, b, l, h, d, scale);
+  return saicv_attn_fwd(&a, stream);
+}
+
+int saicv_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int b,
+                        int l, int h, int d, float scale, void* stream) {
+  saicv_attn_bwd_args a{};
+  fill_packed(&a.fwd, qkv, const_cast<void*>(out), const_cast<float*>(lse), b, l, h, d, scale);
+  a.dout = dout; a.delta = delta;
+  __nv_bfloat16* g = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  a.dq = g; a.dk = g + (long long)h * d; a.dv = g + 2LL * h * d;
+  for (auto* s : {a.dq_strides, a.dk_strides, a.dv_strides}) { s[0] = a.fwd.q_strides[0]; s[1] = d; s[2] = a.fwd.q_strides[2]; }
+  a.dk_cols = d;
+  return saicv_attn_bwd(&a, stream);
+}
+
+}  // extern "C"

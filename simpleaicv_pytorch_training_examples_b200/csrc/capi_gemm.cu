@@ -245,8 +245,10 @@ int saicv_linear_dgrad(const void* dy, const void* w, const float* resid, const 
   p.M = M; p.N = K; p.num_kb = (N + BK - 1) / BK; p.kb_per_split = p.num_kb; p.splits = 1;
   p.a_mode = A_K2D; p.b_mode = B_MN2D;
   p.g.P = p.g.Q = 1; p.g.cchunks = 1; p.g.S = 1; p.g.R = 1;
-  p.epi_flags = (flags & EPI_DIRECT) | (resid ? EPI_RESID : 0) | (gelu_pre ? EPI_MUL_DGELU : 0);
-  if (gelu_pre && !aligned16(gelu_pre)) return set_error("saicv_linear_dgrad: unaligned gelu_pre");
+  // aux bf16 operand [M, K]: SAICV_EPI_MUL_DRELU -> ReLU output (mask), SAICV_EPI_ADD_BF16 -> added, default -> dGELU pre-activation
+  const int aux_mode = !gelu_pre ? 0 : (flags & EPI_MUL_DRELU) ? EPI_MUL_DRELU : (flags & EPI_RESID_BF16) ? EPI_RESID_BF16 : EPI_MUL_DGELU;
+  p.epi_flags = (flags & EPI_DIRECT) | (resid ? EPI_RESID : 0) | aux_mode;
+  if (gelu_pre && !aligned16(gelu_pre)) return set_error("saicv_linear_dgrad: unaligned aux operand");
   p.out_f32 = out_f32; p.resid = resid; p.resid_bf16 = gelu_pre; p.out = dx; p.ldd = K;
   return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream);
 }

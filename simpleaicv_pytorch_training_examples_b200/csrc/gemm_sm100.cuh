@@ -24,7 +24,7 @@ namespace saicv {
 enum : int { A_K2D = 0, A_IM2COL = 1, A_MN2D = 2 };
 enum : int { B_K2D = 0, B_MN2D = 2, B_IM2COL = 3 };
 enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_GELU = 4, EPI_DIRECT = 8, EPI_RESID = 16, EPI_RESID_BF16 = 32,
-              EPI_MUL_DGELU = 64, EPI_ROW_SCALE = 128, EPI_STATS = 256 };
+              EPI_MUL_DGELU = 64, EPI_ROW_SCALE = 128, EPI_STATS = 256, EPI_MUL_DRELU = 512 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -65,7 +65,7 @@ struct GemmParams {
   int out_f32;         // 1: D is fp32, else bf16
   const float* bias;   // [N] or null
   const float* resid;  // fp32 [M, ldd] residual added in the epilogue (EPI_RESID) or null
-  const void* resid_bf16;  // bf16 [M, ldd]: added (EPI_RESID_BF16) or, as pre-activation u, D *= gelu'(u) (EPI_MUL_DGELU)
+  const void* resid_bf16;  // bf16 [M, ldd]: added (EPI_RESID_BF16); as pre-activation u, D *= gelu'(u) (EPI_MUL_DGELU); as ReLU output, D *= (r > 0) (EPI_MUL_DRELU)
   const float* row_scale;  // EPI_ROW_SCALE: D = resid + row_scale[row / rows_per_scale] * (acc + bias) (drop-path)
   int rows_per_scale;
   void* out;           // direct-store path
@@ -321,7 +321,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float4 rf[8];
         uint4 rb[4];
         const bool has_rf = (p.epi_flags & EPI_RESID) && row < p.M;
-        const bool has_rb = (p.epi_flags & (EPI_RESID_BF16 | EPI_MUL_DGELU)) && row < p.M;
+        const bool has_rb = (p.epi_flags & (EPI_RESID_BF16 | EPI_MUL_DGELU | EPI_MUL_DRELU)) && row < p.M;
         float rscale = 1.f;
         if ((p.epi_flags & EPI_ROW_SCALE) && row < p.M) rscale = __ldg(p.row_scale + row / p.rows_per_scale);
         if (has_rf) {
@@ -379,6 +379,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (p.epi_flags & EPI_MUL_DGELU) {
                 f[8 * j + 2 * u] *= gelu_erf_grad(ab.x);
                 f[8 * j + 2 * u + 1] *= gelu_erf_grad(ab.y);
+              } else if (p.epi_flags & EPI_MUL_DRELU) {   // resid_bf16 = ReLU output: pass the gradient where it is > 0
+                f[8 * j + 2 * u] = ab.x > 0.f ? f[8 * j + 2 * u] : 0.f;
+                f[8 * j + 2 * u + 1] = ab.y > 0.f ? f[8 * j + 2 * u + 1] : 0.f;
               } else {
                 f[8 * j + 2 * u] += ab.x;
                 f[8 * j + 2 * u + 1] += ab.y;

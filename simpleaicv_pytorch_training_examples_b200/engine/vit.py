@@ -42,9 +42,14 @@ class _Linear:
         return ops.linear_fwd(x, self.w_bf16, bias=self.b_pad, resid=resid, out_f32=out_f32,
                               row_scale=row_scale, rows_per_scale=rows_per_scale)
 
-    def bwd(self, dy, x, sink, need_dx=True, gelu_pre=None):
+    def fwd_flags(self, x, flags):
+        """Forward with an activation fused in the epilogue (ops.EPI_RELU / ops.EPI_GELU)."""
+        return ops.linear_fwd(x, self.w_bf16, bias=self.b_pad, flags=flags)
+
+    def bwd(self, dy, x, sink, need_dx=True, gelu_pre=None, relu_out=None, add=None):
         """dy bf16 [M, N], x bf16 [M, K]: writes dW, db through the sink, returns dx bf16
-        (multiplied by gelu'(gelu_pre) when the input of this layer was gelu(gelu_pre))."""
+        (multiplied by gelu'(gelu_pre) when the input of this layer was gelu(gelu_pre), masked by
+        relu_out > 0 when it was a ReLU output, plus `add` when a second gradient joins there)."""
         w, b = self.mod.weight, self.mod.bias
         n = w.shape[0]
         wbuf, wacc = sink.begin(w)
@@ -64,7 +69,7 @@ class _Linear:
             ops.colsum(dy, full)
             bbuf.copy_(full[:n] + (bbuf if bacc else 0))
         sink.done(b, bbuf)
-        return ops.linear_dgrad(dy, self.w_bf16, gelu_pre=gelu_pre) if need_dx else None
+        return ops.linear_dgrad(dy, self.w_bf16, gelu_pre=gelu_pre, relu_out=relu_out, add=add) if need_dx else None
 
 
 class _Block:

@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from ._lib import ConvShape
 
-EPI_BIAS, EPI_RELU, EPI_GELU, EPI_DIRECT, EPI_RESID = 1, 2, 4, 8, 16
+EPI_BIAS, EPI_RELU, EPI_GELU, EPI_DIRECT, EPI_RESID, EPI_ADD_BF16, EPI_MUL_DRELU = 1, 2, 4, 8, 16, 32, 512
 
 
 def _p(t):
@@ -53,11 +53,17 @@ def linear_fwd(x, w, bias=None, resid=None, out=None, flags=0, out_f32=False, ro
     return out
 
 
-def linear_dgrad(dy, w, resid=None, out=None, flags=0, out_f32=False, gelu_pre=None):
-    """gelu_pre: bf16 [M, K] pre-activation; the result is multiplied by gelu'(gelu_pre) in the epilogue."""
+def linear_dgrad(dy, w, resid=None, out=None, flags=0, out_f32=False, gelu_pre=None, relu_out=None, add=None):
+    """gelu_pre: bf16 [M, K] pre-activation; the result is multiplied by gelu'(gelu_pre) in the epilogue.
+    relu_out: bf16 [M, K] ReLU output; the result is zeroed where it is <= 0.  add: bf16 [M, K] added."""
     M, N = dy.shape
     K = w.shape[1]
     assert dy.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[0] == N
+    assert (gelu_pre is not None) + (relu_out is not None) + (add is not None) <= 1
+    if relu_out is not None:
+        gelu_pre, flags = relu_out, flags | EPI_MUL_DRELU
+    elif add is not None:
+        gelu_pre, flags = add, flags | EPI_ADD_BF16
     if out is None:
         out = torch.empty(M, K, device=dy.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
     _lib.call('saicv_linear_dgrad', _p(dy), _p(w), _p(resid), _p(gelu_pre), _p(out), M, N, K, flags,
@@ -364,6 +370,7 @@ def token_pool_bwd(dpooled, l, mean_pool, dx=None, dx_bf16=None, bf16_row_scale=
 
 
 def attention_fwd(qkv, b, l, h, d, scale, out=None, lse=None):
+    """Packed-qkv attention of the ViT blocks: qkv bf16 [b*l, 3*h*d] ([b][l][3][h][d]) -> out bf16 [b*l, h*d]."""
     if out is None:
         out = torch.empty(b * l, h * d, device=qkv.device, dtype=torch.bfloat16)
     if lse is None:
@@ -375,5 +382,155 @@ def attention_fwd(qkv, b, l, h, d, scale, out=None, lse=None):
 def attention_bwd(qkv, out, dout, lse, b, l, h, d, scale, dqkv=None):
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
-    _lib.call('saicv_attention_bwd', _p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), b, l, h, d, scale, _stream())
+    delta = torch.empty(b, h, l, device=qkv.device, dtype=torch.float32)
+    _lib.call('saicv_attention_bwd', _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), b, l, h, d, scale, _stream())
     return dqkv
+
+
+def _bhl_strides(t):
+    """Element strides {batch, head, row} of a [B, H, L, D] view whose last dimension is contiguous."""
+    assert t.dim() == 4 and t.stride(3) == 1 and t.dtype == torch.bfloat16 and t.is_cuda
+    return (ctypes.c_longlong * 3)(t.stride(0), t.stride(1), t.stride(2))
+
+
+def pack_key_mask(mask, lk):
+    """bool [B, Lk] (True = padded key, nn.MultiheadAttention's key_padding_mask) -> int32 bit words
+    [B, words] (bit k%32 of word k/32) with words*32 >= lk rounded up to 128."""
+    b = mask.shape[0]
+    words = (lk + 127) // 128 * 4
+    m = torch.zeros(b, words * 32, device=mask.device, dtype=torch.int64)
+    m[:, :lk] = mask.to(torch.int64)
+    w = (m.view(b, words, 32) << torch.arange(32, device=mask.device)).sum(-1)          # 0 .. 2^32-1
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)                                         # same bits as int32
+    return w.to(torch.int32).contiguous()
+
+
+def _attn_args(q, k, v, out, lse, scale, mask_bits):
+    a = _lib.AttnArgs()
+    b, h, lq, dqk = q.shape
+    lk, dv = k.shape[2], v.shape[3]
+    assert k.shape == (b, h, lk, dqk) and v.shape == (b, h, lk, dv) and out.shape == (b, h, lq, dv)
+    a.q, a.k, a.v, a.out, a.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr()
+    a.q_strides, a.k_strides, a.v_strides, a.o_strides = _bhl_strides(q), _bhl_strides(k), _bhl_strides(v), _bhl_strides(out)
+    a.key_mask_bits = mask_bits.data_ptr() if mask_bits is not None else None
+    a.mask_words = mask_bits.shape[1] if mask_bits is not None else 0
+    a.b, a.h, a.lq, a.lk, a.dqk, a.dv, a.scale = b, h, lq, lk, dqk, dv, scale
+    return a
+
+
+def attn_fwd(q, k, v, scale, out=None, mask_bits=None):
+    """General fused attention.  q [B, H, Lq, Dqk], k [B, H, Lk, Dqk], v [B, H, Lk, Dv]: bf16 VIEWS with a
+    contiguous last dimension (any batch / head / row strides).  out: [B, H, Lq, Dv] view to write (default:
+    a [B, Lq, H, Dv] buffer viewed as [B, H, Lq, Dv], i.e. heads concatenated per token).  Returns (out, lse)."""
+    b, h, lq, _ = q.shape
+    dv = v.shape[3]
+    if out is None:
+        out = torch.empty(b, lq, h, dv, device=q.device, dtype=torch.bfloat16).permute(0, 2, 1, 3)
+    lse = torch.empty(b, h, lq, device=q.device, dtype=torch.float32)
+    a = _attn_args(q, k, v, out, lse, scale, mask_bits)
+    _lib.call('saicv_attn_fwd', ctypes.byref(a), _stream())
+    return out, lse
+
+
+def attn_bwd(q, k, v, out, lse, dout, scale, dq, dk, dv, dk_cols=0, mask_bits=None):
+    """Gradients of attn_fwd written into the given [B, H, L, D] views dq (Dqk cols), dk (leading dk_cols
+    columns; 0 = all) and dv."""
+    assert dout.stride() == out.stride(), 'dout must have the layout of out'
+    a = _lib.AttnBwdArgs()
+    a.fwd = _attn_args(q, k, v, out, lse, scale, mask_bits)
+    delta = torch.empty_like(lse)
+    a.dout, a.delta = dout.data_ptr(), delta.data_ptr()
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.dq_strides, a.dk_strides, a.dv_strides = _bhl_strides(dq), _bhl_strides(dk), _bhl_strides(dv)
+    a.dk_cols = dk_cols
+    _lib.call('saicv_attn_bwd', ctypes.byref(a), _stream())
+    return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------- VAN kernels
+def dwconv_fwd(x, w, bias, k, dil=1, relu=False, flip=False):
+    """Depthwise k x k 'same' convolution on NHWC bf16; w fp32 [C, 1, k, k]; flip=True gives the data gradient."""
+    n, h, wd, c = x.shape
+    out = torch.empty_like(x)
+    _lib.call('saicv_dwconv_fwd', _p(x), _p(w), _p(bias), _p(out), n, h, wd, c, k, dil, int(relu), int(flip), _stream())
+    return out
+
+
+def dwconv_wgrad(dy, x, dw, k, dil=1, accumulate=False):
+    n, h, wd, c = x.shape
+    nblk = _lib.load().saicv_dwconv_wgrad_blocks(n * h * wd)
+    partial = torch.empty(nblk * k * k * c, device=x.device, dtype=torch.float32)
+    _lib.call('saicv_dwconv_wgrad', _p(dy), _p(x), _p(partial), _p(dw), n, h, wd, c, k, dil, int(accumulate), _stream())
+    return dw
+
+
+def mul_bf16(a, b):
+    out = torch.empty_like(a)
+    _lib.call('saicv_mul_bf16', _p(a), _p(b), _p(out), a.numel(), _stream())
+    return out
+
+
+def gate_bwd(dg, c1, dlk, p1):
+    out = torch.empty_like(dg)
+    _lib.call('saicv_gate_bwd', _p(dg), _p(c1), _p(dlk), _p(p1), _p(out), dg.numel(), _stream())
+    return out
+
+
+def ls_residual_fwd(x, branch, shortcut, ls, row_scale=None, rows_per_scale=0):
+    c = x.shape[-1]
+    rows = x.numel() // c
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _lib.call('saicv_ls_residual_fwd', _p(x), int(x.dtype == torch.float32), _p(branch), _p(shortcut), _p(ls), _p(row_scale),
+              rows_per_scale, _p(out), rows, c, _stream())
+    return out
+
+
+def ls_residual_bwd(dxn, branch, shortcut, ls, dls, accumulate=False, row_scale=None, rows_per_scale=0):
+    c = dxn.shape[-1]
+    rows = dxn.numel() // c
+    dy = torch.empty(dxn.shape, device=dxn.device, dtype=torch.bfloat16)
+    _lib.call('saicv_ls_residual_bwd', _p(dxn), _p(branch), _p(shortcut), _p(ls), _p(row_scale), rows_per_scale, _p(dy),
+              _p(partial_ws(dxn.device, 2 * c)), _p(dls), rows, c, int(accumulate), _stream())
+    return dy
+
+
+def bn_stats_generic(x):
+    """Partial sums for bn_finalize (pass partial_rows=bn_generic_rows(rows, c))."""
+    c = x.shape[-1]
+    rows = x.numel() // c
+    partial = partial_ws(x.device, 2 * c)
+    _lib.call('saicv_bn_stats_generic', _p(x), int(x.dtype == torch.float32), _p(partial), rows, c, _stream())
+    return partial, _lib.load().saicv_bn_generic_partial_rows(rows, c)
+
+
+def bn_apply_generic(x, scale_shift, out_f32):
+    c = x.shape[-1]
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    _lib.call('saicv_bn_apply_generic', _p(x), int(x.dtype == torch.float32), _p(scale_shift), _p(out), int(out_f32),
+              x.numel() // c, c, _stream())
+    return out
+
+
+def bn_bwd_generic(x, g, saved, gamma, dgamma, dbeta, dres=None, dx_f32=True, accumulate=False):
+    c = x.shape[-1]
+    rows = x.numel() // c
+    dx = torch.empty(x.shape, device=x.device, dtype=torch.float32 if dx_f32 else torch.bfloat16)
+    sums = torch.empty(2 * c, device=x.device, dtype=torch.float32)
+    _lib.call('saicv_bn_bwd_generic', _p(x), int(x.dtype == torch.float32), _p(g), int(g.dtype == torch.float32), _p(saved),
+              _p(gamma), _p(dres), _p(partial_ws(x.device, 2 * c)), _p(sums), _p(dx), int(dx_f32), _p(dgamma), _p(dbeta),
+              rows, c, int(accumulate), _stream())
+    return dx
+
+
+def im2col_nhwc(x, k, stride, pad):
+    n, h, w, c = x.shape
+    P, Q = conv_out_size(h, pad, k, stride), conv_out_size(w, pad, k, stride)
+    cols = torch.empty(n * P * Q, k * k * c, device=x.device, dtype=torch.bfloat16)
+    _lib.call('saicv_im2col_nhwc', _p(x), _p(cols), n, h, w, c, k, stride, pad, _stream())
+    return cols, P, Q
+
+
+def col2im_nhwc(dcols, n, h, w, c, k, stride, pad):
+    dx = torch.empty(n, h, w, c, device=dcols.device, dtype=torch.bfloat16)
+    _lib.call('saicv_col2im_nhwc', _p(dcols), _p(dx), n, h, w, c, k, stride, pad, _stream())
+    return dx

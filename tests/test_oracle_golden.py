@@ -52,4 +52,4 @@ def test_oracle_reproduces_reference_outputs(path):
 
 def test_golden_fixtures_cover_every_built_family():
     fams = {load_fixture(p)['family'] for p in GOLDEN}
-    assert {'resnet', 'vit', 'darknet'} <= fams, fams
+    assert {'resnet', 'vit', 'darknet', 'van'} <= fams, fams

@@ -114,3 +114,30 @@ def test_b200_vit_constructors_match_reference_state_dict(arch, kw):
     assert list(rs.keys()) == list(ms.keys())
     assert all(torch.equal(rs[k], ms[k]) for k in rs)
     assert [n for n, _ in ref.named_parameters()] == [n for n, _ in m.named_parameters()]
+
+
+@pytest.mark.parametrize('arch', ['van_b0'])
+def test_van_oracle_and_constructor_match_reference(arch):
+    """oracle/van.py and the B200 constructor shell vs van.py:211-310 (seeded init, logits, every gradient)."""
+    from oracle import van
+    from simpleaicv_pytorch_training_examples_b200.classification import backbones as mine
+    torch.manual_seed(6)
+    ref = _ref_backbones().__dict__[arch](num_classes=10)
+    torch.manual_seed(6)
+    m = mine.__dict__[arch](num_classes=10)
+    sd = van.init_state(arch, 10, 6)
+    rs, ms = ref.state_dict(), m.state_dict()
+    assert list(rs.keys()) == list(ms.keys()) == list(sd.keys())
+    assert all(torch.equal(rs[k], ms[k]) and torch.equal(rs[k], sd[k]) for k in rs)
+    assert [n for n, _ in ref.named_parameters()] == [n for n, _ in m.named_parameters()]
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    y = torch.randint(0, 10, (2,), generator=g)
+    ref.train()
+    out = ref(x)
+    torch.nn.functional.cross_entropy(out.float(), y).backward()
+    lo, _, gr = van.loss_and_grads(sd, x, y, arch)
+    torch.testing.assert_close(lo, out.detach(), rtol=1e-5, atol=1e-6)
+    for n, p in ref.named_parameters():
+        rel = ((gr[n] - p.grad).norm() / p.grad.norm().clamp_min(1e-20)).item()
+        assert rel < 1e-4 or (gr[n] - p.grad).abs().max().item() < 1e-7, (n, rel)
