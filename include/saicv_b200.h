@@ -237,6 +237,27 @@ int saicv_im2col_nhwc(const void* x, void* cols, int n, int h, int w, int c, int
 int saicv_col2im_nhwc(const void* dcols, void* dx, int n, int h, int w, int c, int k, int stride, int pad,
                       void* stream);
 
+/* ---- SAM image encoder (segment_anything/image_encoder.py) ---------------------------------------------
+ * Window partition with zero padding (:32-55) / unpartition (:58-79) of NHWC bf16 tokens:
+ * windows [b*nwy*nwx][ws*ws][c], nwy = ceil(h/ws), nwx = ceil(w/ws). */
+int saicv_window_partition(const void* x, void* windows, int b, int h, int w, int c, int ws, void* stream);
+int saicv_window_unpartition(const void* windows, void* x, int b, int h, int w, int c, int ws, void* stream);
+/* x[b][...] += pos[...] (fp32, in place): tokens + pos_embed (:315); per_batch = elements of pos. */
+int saicv_add_pos_embed(float* x, const float* pos, int b, long long per_batch, void* stream);
+/* Decomposed relative-position bias (:82-144) as extra score columns for saicv_attn_fwd (scale 1):
+ *   qe[bw][head][l] = [q*scale | rel_h[l][0..sh) | rel_w[l][0..sw) | 0..],  ke = [k | onehot(kh) | onehot(kw) | 0..]
+ * from packed qkv bf16 [bw][sh*sw][3][heads][hd] and the fp32 tables rel_pos_h [2sh-1][hd], rel_pos_w
+ * [2sw-1][hd]; rows of qe / ke have dqk >= hd + sh + sw (multiple of 16) elements. */
+int saicv_relpos_build(const void* qkv, const float* rel_pos_h, const float* rel_pos_w, void* qe, void* ke,
+                       int bw, int heads, int hd, int sh, int sw, int dqk, float scale, void* stream);
+/* Backward: dqe (gradient of qe from saicv_attn_bwd) -> dq into the q slot of dqkv (layout of qkv), and
+ * d_rel_pos_h / d_rel_pos_w (+)=.  partial: fp32 workspace
+ * (saicv_relpos_bwd_blocks(rows) + 1) * ((2sh-1) + (2sw-1)) * hd floats, rows = bw*heads*sh*sw. */
+int saicv_relpos_bwd_blocks(long long rows);
+int saicv_relpos_bwd(const void* dqe, const void* qkv, const float* rel_pos_h, const float* rel_pos_w,
+                     void* dqkv, float* partial, float* d_rel_pos_h, float* d_rel_pos_w, int bw, int heads,
+                     int hd, int sh, int sw, int dqk, float scale, int accumulate, void* stream);
+
 /* ---- fused multi-head attention on tcgen05 / TMEM (csrc/attn_sm100.cuh) ------------------------------
  * Replaces the materialised attention of the reference: vit.py:62-80 (q k^T * scale, softmax, @ v),
  * segment_anything/image_encoder.py:167-184 (+ decomposed rel-pos bias, folded into extra score columns by
@@ -248,7 +269,7 @@ int saicv_col2im_nhwc(const void* dcols, void* dx, int n, int h, int w, int c, i
  *   qkv [b][l][3][h][d], [b*h][l][d] and [b][l][h*d] layouts are all views.  lse [b][h][lq] fp32 holds
  *   log2(sum exp2(s*scale*log2e)) for the backward.  key_mask_bits: [b][mask_words] uint32, bit k%32 of
  *   word k/32 set = key k is padding (NULL: none); mask_words*32 >= lk rounded up to 128.
- *   Supported (dqk, dv): (32,32) (64,64) (80,80) (96,64) (112,80) (192,64) (208,80). */
+ *   Supported (dqk, dv): (32,32) (64,64) (80,80) (96,64) (112,64) (112,80) (128,80) (192,64) (208,80). */
 typedef struct {
   const void* q; const void* k; const void* v;
   void* out;

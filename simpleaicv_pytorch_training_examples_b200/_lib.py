@@ -86,6 +86,12 @@ SIGNATURES = {
     'saicv_attn_fwd': [ctypes.POINTER(AttnArgs), c_void_p],
     'saicv_attn_bwd': [ctypes.POINTER(AttnBwdArgs), c_void_p],
     'saicv_attn_error': [],
+    'saicv_window_partition': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_window_unpartition': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'saicv_add_pos_embed': [c_void_p, c_void_p, c_int, c_ll, c_void_p],
+    'saicv_relpos_build': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    'saicv_relpos_bwd_blocks': [c_ll],
+    'saicv_relpos_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     'saicv_dwconv_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     'saicv_dwconv_wgrad_blocks': [c_ll],
     'saicv_dwconv_wgrad': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],

@@ -64,6 +64,37 @@ __device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t a_addr, uint3
   }
 }
 
+// running maximum over one 32-column chunk of raw scores; `dead` bit i set = column i is padding / masked
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], uint32_t dead, float mx) {
+  if (dead == 0) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((dead >> i) & 1u) ? -INFINITY : __uint_as_float(v[i]));
+  }
+  return mx;
+}
+// e = exp2(s * sl - msl) for one 32-column chunk (0 where dead), packed to bf16 into the 128B-swizzled A tile:
+// 16-byte pieces piece0 .. piece0+3 of this thread's 128-byte row (row & 7 == sw).  Returns rs + sum(e).
+__device__ __forceinline__ float chunk_exp_store(const uint32_t (&v)[32], uint32_t dead, float sl, float msl, float rs,
+                                                 uint8_t* row_base, int piece0, int sw) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {   // 8 columns -> one 16-byte piece
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[8 * t + i]), sl, -msl));
+    if (dead != 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[i] = ((dead >> (8 * t + i)) & 1u) ? 0.f : e[i];
+    }
+    rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+    *reinterpret_cast<uint4*>(row_base + (((piece0 + t) ^ sw) << 4)) =
+        make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+  }
+  return rs;
+}
+
 template <int DQK, int DV, int MINB>
 struct AttnFwdCfg {
   static constexpr int BN = 128;
@@ -71,15 +102,20 @@ struct AttnFwdCfg {
   static constexpr int QBYTES = NCQ * 16384, KBYTES = NCQ * BN * 128, VBYTES = NCV * BN * 128, PBYTES = (BN / 64) * 16384;
   static constexpr int kStages = (QBYTES + 2 * (KBYTES + VBYTES) + PBYTES + 256 <= 232448) ? 2 : 1;   // K / V ring depth
   static constexpr int kSmemBytes = QBYTES + kStages * (KBYTES + VBYTES) + PBYTES + 256;
-  static constexpr int kTmemCols = 256;   // S: columns 0..127, O block: 128..128+DV
+  static constexpr int OCOLS = ((DV + 31) & ~31);   // O accumulator columns
+  static constexpr int kTmemCols = 256;             // S: columns 0..127, O: 128..128+OCOLS
 };
 
+// Forward.  Numerics: P = exp2((s - m_ref) * scale_log2) with a per-row reference m_ref that is only raised when a
+// block's scores exceed it by more than 2^8 (lazy rescaling): O and the row sums then stay in TMEM across key
+// blocks (accumulating MMAs) and are read once per work item; a raise multiplies both by 2^((m_old - m_new) * scale_log2)
+// in TMEM (rare); the row sums live in registers and follow the same rescaling.
 template <int DQK, int DV, int MINB>
 __global__ void __launch_bounds__(kAttnThreads, MINB)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using Cfg = AttnFwdCfg<DQK, DV, MINB>;
-  constexpr int BN = Cfg::BN, NCQ = Cfg::NCQ, NCV = Cfg::NCV, kStages = Cfg::kStages;
+  constexpr int BN = Cfg::BN, NCQ = Cfg::NCQ, NCV = Cfg::NCV, kStages = Cfg::kStages, OCOLS = Cfg::OCOLS;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::QBYTES;
@@ -92,11 +128,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* k_empty = k_full + kStages;
   uint64_t* v_full = k_empty + kStages;
   uint64_t* v_empty = v_full + kStages;
-  uint64_t* s_full = v_empty + kStages;
-  uint64_t* s_empty = s_full + 1;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_full = s_full + 3;
-  uint64_t* o_empty = s_full + 4;
+  uint64_t* s_full = v_empty + kStages;     // S_j in TMEM
+  uint64_t* s_empty = s_full + 1;           // S_j consumed by the softmax warps
+  uint64_t* p_full = s_full + 2;            // P_j in shared memory
+  uint64_t* pv_done = s_full + 3;           // P_j V_j has completed (once per key block)
+  uint64_t* o_empty = s_full + 4;           // O / l of the work item read out (once per work item)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,7 +155,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_init(s_full, 1);
     mbar_init(s_empty, 4);
     mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
+    mbar_init(pv_done, 1);
     mbar_init(o_empty, 4);
     fence_barrier_init();
   }
@@ -165,30 +201,38 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, BN, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, DV, 0, 1);
-      uint32_t it = 0, g = 0;
+      uint32_t it = 0, gs = 0, gp = 0;   // work items, score blocks issued, P V blocks issued (per-CTA stream counters)
+      // S for block j of the current item: only needs K_j and the softmax warps to have COPIED S_{j-1} out of TMEM, so it
+      // is issued ahead of P_{j-1} V_{j-1} and runs on the tensor core while the exponentials of block j-1 are computed.
+      auto issue_s = [&](int j) {
+        const int st = gs % kStages;
+        const uint32_t ph = (gs / kStages) & 1;
+        const int nj = (min(BN, p.Lk - j * BN) + 15) & ~15;
+        mbar_wait(&k_full[st], ph);
+        mbar_wait(s_empty, (gs & 1) ^ 1);
+        tc_fence_after();
+        issue_scores<DQK>(tmem_S, smem_u32(sQ), 16384, smem_u32(sK + st * Cfg::KBYTES), BN * 128, idesc_with_n(idesc_s, nj));
+        umma_commit(&k_empty[st]);
+        umma_commit(s_full);
+        if (j == nkb - 1) umma_commit(q_empty);
+        ++gs;
+      };
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
         mbar_wait(q_full, it & 1);
-        for (int j = 0; j < nkb; ++j, ++g) {
-          const int st = g % kStages;
-          const uint32_t ph = (g / kStages) & 1;
-          const int nvalid = min(BN, p.Lk - j * BN);
-          const int nj = (nvalid + 15) & ~15;
-          // ---- S_j = Q K_j^T
-          mbar_wait(&k_full[st], ph);
-          mbar_wait(s_empty, (g & 1) ^ 1);
-          tc_fence_after();
-          issue_scores<DQK>(tmem_S, smem_u32(sQ), 16384, smem_u32(sK + st * Cfg::KBYTES), BN * 128, idesc_with_n(idesc_s, nj));
-          umma_commit(&k_empty[st]);
-          umma_commit(s_full);
-          if (j == nkb - 1) umma_commit(q_empty);
-          // ---- O_blk = P_j V_j
+        issue_s(0);
+        for (int j = 0; j < nkb; ++j, ++gp) {
+          if (j + 1 < nkb) issue_s(j + 1);
+          // ---- O (+)= P_j V_j
+          const int st = gp % kStages;
+          const uint32_t ph = (gp / kStages) & 1;
+          const int nj = (min(BN, p.Lk - j * BN) + 15) & ~15;
           mbar_wait(&v_full[st], ph);
-          mbar_wait(p_full, g & 1);
-          mbar_wait(o_empty, (g & 1) ^ 1);
+          if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);   // the previous item's O has been read out
+          mbar_wait(p_full, gp & 1);
           tc_fence_after();
-          issue_pv(tmem_O, smem_u32(sP), smem_u32(sV + st * Cfg::VBYTES), BN * 128, nj, idesc_o, false);
+          issue_pv(tmem_O, smem_u32(sP), smem_u32(sV + st * Cfg::VBYTES), BN * 128, nj, idesc_o, j > 0);
           umma_commit(&v_empty[st]);
-          umma_commit(o_full);
+          umma_commit(pv_done);
         }
       }
     }
@@ -200,101 +244,101 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     uint8_t* const prow = sP + row * 128;
     const int sw = row & 7;
+    const float thr_raw = 8.0f / p.scale_log2;        // raise the reference only past a factor 2^8
     uint32_t g = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int qt = w % p.num_q_tiles, bh = w / p.num_q_tiles, b = bh / p.H, h = bh % p.H;
-      float m = -INFINITY, l = 0.f;
-      float o[DV];
-#pragma unroll
-      for (int i = 0; i < DV; ++i) o[i] = 0.f;
+      float m_ref = -INFINITY, l = 0.f;               // reference in raw-score units; row sum relative to it
       for (int j = 0; j < nkb; ++j, ++g) {
         const int nvalid = min(BN, p.Lk - j * BN);
         const int nchunks = (nvalid + 31) >> 5;
-        mbar_wait(s_full, g & 1);
-        tc_fence_after();
-        // ---- pass 1: row maximum (scores in the log2 domain)
-        float mx = -INFINITY;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_S + lane_off + c * 32, v);
-          tmem_ld_wait();
-          uint32_t dead = 0;  // bit j set: column is padding or masked
-          const int rem = nvalid - c * 32;
-          if (rem < 32) dead = 0xffffffffu << rem;
-          if (p.mask_bits) dead |= __ldg(p.mask_bits + (long long)b * p.mask_words + ((j * BN) >> 5) + c);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float s = __uint_as_float(v[i]) * p.scale_log2;
-            mx = fmaxf(mx, ((dead >> i) & 1u) ? -INFINITY : s);
-          }
-        }
-        const float m_new = fmaxf(m, mx);
-        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;   // fully masked so far: keep everything at zero
-        const float alpha = ex2_approx(m - m_use);
-        // ---- pass 2: P = exp2(s - m), row sum, bf16 P into the swizzled A-operand tile
-        float rs = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_S + lane_off + c * 32, v);
-          tmem_ld_wait();
-          if (c == nchunks - 1) {  // S fully consumed: the MMA warp may overwrite it with the next block's scores
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty);
-          }
+        auto dead_bits = [&](int c) -> uint32_t {
           uint32_t dead = 0;
           const int rem = nvalid - c * 32;
           if (rem < 32) dead = 0xffffffffu << rem;
           if (p.mask_bits) dead |= __ldg(p.mask_bits + (long long)b * p.mask_words + ((j * BN) >> 5) + c);
-          float pv[32];
+          return dead;
+        };
+        mbar_wait(s_full, g & 1);
+        tc_fence_after();
+        // All of S_j goes to registers with ONE wait (TMEM load latency is paid once per block); the TMEM S buffer is
+        // handed back at once, so the tensor core computes S_{j+1} while this block's exponentials are evaluated.
+        uint32_t v[4][32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = ex2_approx(__uint_as_float(v[i]) * p.scale_log2 - m_use);
-            pv[i] = ((dead >> i) & 1u) ? 0.f : e;
-            rs += pv[i];
-          }
-          uint8_t* const dst = prow + (c >> 1) * 16384;
+        for (int c = 0; c < 4; ++c)
+          if (c < nchunks) tmem_ld_32x32(tmem_S + lane_off + c * 32, v[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty);
+        uint32_t dead[4];
+        float bm = -INFINITY;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int piece = (c & 1) * 4 + t;
-            *reinterpret_cast<uint4*>(dst + ((piece ^ sw) << 4)) =
-                make_uint4(pack_bf16x2(pv[8 * t], pv[8 * t + 1]), pack_bf16x2(pv[8 * t + 2], pv[8 * t + 3]),
-                           pack_bf16x2(pv[8 * t + 4], pv[8 * t + 5]), pack_bf16x2(pv[8 * t + 6], pv[8 * t + 7]));
+        for (int c = 0; c < 4; ++c)
+          if (c < nchunks) {
+            dead[c] = dead_bits(c);
+            bm = chunk_max(v[c], dead[c], bm);
           }
+        // P_{g-1} V_{g-1} must have finished before the P tile is overwritten (and before O is touched below)
+        if (g > 0) mbar_wait(pv_done, (g - 1) & 1);
+        tc_fence_after();
+        // lazy reference: raise it only when this block exceeds it by more than 2^8 (always on the first valid score)
+        const bool raise = bm > m_ref + thr_raw;
+        if (__any_sync(0xffffffffu, raise)) {
+          const bool had_ref = m_ref != -INFINITY;
+          const float corr = (raise && had_ref) ? ex2_approx((m_ref - bm) * p.scale_log2) : 1.f;
+          l *= corr;
+          if (j > 0 && __any_sync(0xffffffffu, raise && had_ref)) {   // blocks < j sit in TMEM relative to the old reference
+#pragma unroll 1
+            for (int c2 = 0; c2 < OCOLS / 32; ++c2) {
+              uint32_t t[32];
+              tmem_ld_32x32(tmem_O + lane_off + c2 * 32, t);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * corr);
+              tmem_st_32x32(tmem_O + lane_off + c2 * 32, t);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+          }
+          if (raise) m_ref = bm;
         }
+        const float msl = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
+        float rs = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < nchunks) rs = chunk_exp_store(v[c], dead[c], p.scale_log2, msl, rs, prow + (c >> 1) * 16384, (c & 1) * 4, sw);
+        l += rs;
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
-        l = l * alpha + rs;
-        m = m_new;
-        // ---- O = O * alpha + P_j V_j
-        mbar_wait(o_full, g & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < (DV + 31) / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_O + lane_off + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < DV) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(v[i]);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty);
       }
-      // ---- epilogue: normalise, store the row and its log-sum-exp
+      // ---- epilogue: wait for the last P V, read O and l once, normalise, store the row and its log-sum-exp
+      mbar_wait(pv_done, (g - 1) & 1);
+      tc_fence_after();
+      const float inv = l > 0.f ? __fdividef(1.f, l) : 0.f;
       const int qrow = qt * 128 + row;
-      if (qrow < p.Lq) {
-        const float inv = l > 0.f ? __fdividef(1.f, l) : 0.f;
-        __nv_bfloat16* orow = p.out + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)qrow * p.o_sl;
+      __nv_bfloat16* orow = p.out + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)qrow * p.o_sl;
 #pragma unroll
-        for (int i = 0; i < DV; i += 8)
-          *reinterpret_cast<uint4*>(orow + i) =
-              make_uint4(pack_bf16x2(o[i] * inv, o[i + 1] * inv), pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv),
-                         pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv), pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv));
-        p.lse[((long long)b * p.H + h) * p.Lq + qrow] = m + log2f(l);
+      for (int c = 0; c < (DV + 31) / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_O + lane_off + c * 32, v);
+        tmem_ld_wait();
+        if (qrow < p.Lq) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8)
+            if (c * 32 + i < DV)
+              *reinterpret_cast<uint4*>(orow + c * 32 + i) =
+                  make_uint4(pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv),
+                             pack_bf16x2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv),
+                             pack_bf16x2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv),
+                             pack_bf16x2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv));
+        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      if (qrow < p.Lq) p.lse[((long long)b * p.H + h) * p.Lq + qrow] = l > 0.f ? m_ref * p.scale_log2 + log2f(l) : -INFINITY;
     }
   }
   tc_fence_before();
@@ -435,26 +479,33 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_con
       const uint32_t idesc_s = make_idesc_bf16(128, BN, 0, 0);
       const uint32_t idesc_dq = make_idesc_bf16(128, DQK, 0, 1);    // phase A: dQ += dS K     (N = DQK)
       const uint32_t idesc_dv = make_idesc_bf16(128, DV, 0, 1);     // phase B: dV += P^T dO   (N = DV)
-      uint32_t it = 0, g = 0;
+      uint32_t it = 0, gs = 0, ga = 0;   // work items, score blocks issued, accumulate blocks issued
+      const uint32_t idesc_dk = make_idesc_bf16(128, p.dk_cols, 0, 1);   // phase B: dK += dS^T Q (N = dk_cols)
+      // scores + dP of column block j: issued as soon as the elementwise warps have copied block j-1 out of TMEM, i.e.
+      // ahead of the accumulate GEMMs of block j-1, so the tensor core works while the exponentials are evaluated
+      auto issue_sp = [&](int j) {
+        const int st = gs % kStages;
+        const uint32_t ph = (gs / kStages) & 1;
+        const int nj = (min(BN, Lcol - j * BN) + 15) & ~15;
+        mbar_wait(&c_full[st], ph);
+        mbar_wait(sp_empty, (gs & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t c0 = smem_u32(sC0 + st * Cfg::C0BYTES), c1 = smem_u32(sC1 + st * Cfg::C1BYTES);
+        issue_scores<DQK>(tmem_S, smem_u32(sR0), 16384, c0, 8192, idesc_with_n(idesc_s, nj));
+        issue_scores<DV>(tmem_dP, smem_u32(sR1), 16384, c1, 8192, idesc_with_n(idesc_s, nj));
+        umma_commit(sp_full);
+        ++gs;
+      };
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const uint32_t idesc_dk = make_idesc_bf16(128, p.dk_cols, 0, 1);   // phase B: dK += dS^T Q (N = dk_cols)
         mbar_wait(r_full, it & 1);
-        mbar_wait(acc_empty, (it & 1) ^ 1);
-        for (int j = 0; j < ncb; ++j, ++g) {
-          const int st = g % kStages;
-          const uint32_t ph = (g / kStages) & 1;
-          const int nvalid = min(BN, Lcol - j * BN);
-          const int nj = (nvalid + 15) & ~15;
-          mbar_wait(&c_full[st], ph);
-          mbar_wait(sp_empty, (g & 1) ^ 1);
-          tc_fence_after();
+        issue_sp(0);
+        for (int j = 0; j < ncb; ++j, ++ga) {
+          if (j + 1 < ncb) issue_sp(j + 1);
+          const int st = ga % kStages;
+          const int nj = (min(BN, Lcol - j * BN) + 15) & ~15;
           const uint32_t c0 = smem_u32(sC0 + st * Cfg::C0BYTES), c1 = smem_u32(sC1 + st * Cfg::C1BYTES);
-          // scores and dP (row tile x column block), reduction over the head dimension
-          issue_scores<DQK>(tmem_S, smem_u32(sR0), 16384, c0, 8192, idesc_with_n(idesc_s, nj));
-          issue_scores<DV>(tmem_dP, smem_u32(sR1), 16384, c1, 8192, idesc_with_n(idesc_s, nj));
-          umma_commit(sp_full);
-          // accumulate GEMMs, reduction over the column block
-          mbar_wait(a_full, g & 1);
+          if (j == 0) mbar_wait(acc_empty, (it & 1) ^ 1);    // the previous item's accumulators have been read out
+          mbar_wait(a_full, ga & 1);
           tc_fence_after();
           if (!ROWS_ARE_KEYS) {
             issue_pv(tmem_acc0, smem_u32(sA0), c0, 8192, nj, idesc_dq, j > 0);             // dQ += dS K_j
@@ -507,50 +558,70 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_con
           named_bar_sync(1, 128);
         }
         mbar_wait(sp_full, g & 1);
-        mbar_wait(a_empty, (g & 1) ^ 1);     // the accumulate MMAs of the previous block have read the A tiles
         tc_fence_after();
+        // S and dP of the block go to registers with one wait; TMEM is handed back immediately (the MMA warp then
+        // computes the next block's scores while this block's exponentials run)
+        const int nchunks = (nvalid + 31) >> 5;
+        uint32_t sv[2][32], dv[2][32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          if (c < nchunks) {
+            tmem_ld_32x32(tmem_S + lane_off + c * 32, sv[c]);
+            tmem_ld_32x32(tmem_dP + lane_off + c * 32, dv[c]);
+          }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sp_empty);
+        mbar_wait(a_empty, (g & 1) ^ 1);     // the accumulate MMAs of the previous block have read the A tiles
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t sv[32], dv[32];
-          tmem_ld_32x32(tmem_S + lane_off + c * 32, sv);
-          tmem_ld_32x32(tmem_dP + lane_off + c * 32, dv);
-          tmem_ld_wait();
-          if (c == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sp_empty);
-          }
+          if (c >= nchunks) continue;          // (nj <= 32: the accumulate GEMMs do not read these columns)
           uint32_t dead = 0;
           const int rem = nvalid - c * 32;
-          if (rem < 32) dead = rem <= 0 ? 0xffffffffu : (0xffffffffu << rem);
+          if (rem < 32) dead = 0xffffffffu << rem;
           if (!ROWS_ARE_KEYS && p.mask_bits)
             dead |= __ldg(p.mask_bits + (long long)b * p.mask_words + ((j * BN) >> 5) + c);
           if (!row_ok || row_masked) dead = 0xffffffffu;
-          float pp[32], ds[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float ls = ROWS_ARE_KEYS ? sLse[c * 32 + i] : lse_r;
-            const float dl = ROWS_ARE_KEYS ? sLse[64 + c * 32 + i] : dl_r;
-            float e = ex2_approx(__uint_as_float(sv[i]) * p.scale_log2 - ls);
-            e = ((dead >> i) & 1u) ? 0.f : e;
-            pp[i] = e;
-            ds[i] = e * (__uint_as_float(dv[i]) - dl) * p.scale;
-          }
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int piece = c * 4 + t;
-            uint8_t* const d0 = sA0 + row * 128 + ((piece ^ sw) << 4);
+          for (int t = 0; t < 4; ++t) {        // 8 columns -> one 16-byte piece of P (/ P^T) and dS (/ dS^T)
+            float pp[8], ds[8];
             if (ROWS_ARE_KEYS) {
-              *reinterpret_cast<uint4*>(d0) =
-                  make_uint4(pack_bf16x2(pp[8 * t], pp[8 * t + 1]), pack_bf16x2(pp[8 * t + 2], pp[8 * t + 3]),
-                             pack_bf16x2(pp[8 * t + 4], pp[8 * t + 5]), pack_bf16x2(pp[8 * t + 6], pp[8 * t + 7]));
-              *reinterpret_cast<uint4*>(sA1 + row * 128 + ((piece ^ sw) << 4)) =
-                  make_uint4(pack_bf16x2(ds[8 * t], ds[8 * t + 1]), pack_bf16x2(ds[8 * t + 2], ds[8 * t + 3]),
-                             pack_bf16x2(ds[8 * t + 4], ds[8 * t + 5]), pack_bf16x2(ds[8 * t + 6], ds[8 * t + 7]));
+              const float4 L0 = *reinterpret_cast<const float4*>(sLse + c * 32 + 8 * t);
+              const float4 L1 = *reinterpret_cast<const float4*>(sLse + c * 32 + 8 * t + 4);
+              const float4 D0 = *reinterpret_cast<const float4*>(sLse + 64 + c * 32 + 8 * t);
+              const float4 D1 = *reinterpret_cast<const float4*>(sLse + 64 + c * 32 + 8 * t + 4);
+              const float ls[8] = {L0.x, L0.y, L0.z, L0.w, L1.x, L1.y, L1.z, L1.w};
+              const float dl[8] = {D0.x, D0.y, D0.z, D0.w, D1.x, D1.y, D1.z, D1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                pp[i] = ex2_approx(fmaf(__uint_as_float(sv[c][8 * t + i]), p.scale_log2, -ls[i]));
+                ds[i] = pp[i] * (__uint_as_float(dv[c][8 * t + i]) - dl[i]);
+              }
             } else {
-              *reinterpret_cast<uint4*>(d0) =
-                  make_uint4(pack_bf16x2(ds[8 * t], ds[8 * t + 1]), pack_bf16x2(ds[8 * t + 2], ds[8 * t + 3]),
-                             pack_bf16x2(ds[8 * t + 4], ds[8 * t + 5]), pack_bf16x2(ds[8 * t + 6], ds[8 * t + 7]));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                pp[i] = ex2_approx(fmaf(__uint_as_float(sv[c][8 * t + i]), p.scale_log2, -lse_r));
+                ds[i] = pp[i] * (__uint_as_float(dv[c][8 * t + i]) - dl_r);
+              }
+            }
+            if (dead != 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const bool dd = (dead >> (8 * t + i)) & 1u;
+                pp[i] = dd ? 0.f : pp[i];
+                ds[i] = dd ? 0.f : ds[i];
+              }
+            }
+            const int piece = c * 4 + t;
+            const uint4 dsv = make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]),
+                                         pack_bf16x2(ds[6], ds[7]));
+            if (ROWS_ARE_KEYS) {
+              *reinterpret_cast<uint4*>(sA0 + row * 128 + ((piece ^ sw) << 4)) =
+                  make_uint4(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]), pack_bf16x2(pp[4], pp[5]), pack_bf16x2(pp[6], pp[7]));
+              *reinterpret_cast<uint4*>(sA1 + row * 128 + ((piece ^ sw) << 4)) = dsv;
+            } else {
+              *reinterpret_cast<uint4*>(sA0 + row * 128 + ((piece ^ sw) << 4)) = dsv;
             }
           }
         }
@@ -568,6 +639,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_con
           uint32_t v[32];
           tmem_ld_32x32(tmem_acc0 + lane_off + c * 32, v);
           tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * p.scale);
           if (row_ok) {
 #pragma unroll
             for (int i = 0; i < 32; i += 8)
@@ -604,6 +677,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_con
             uint32_t v[32];
             tmem_ld_32x32(tmem_acc1 + lane_off + c * 32, v);
             tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * p.scale);
             if (row_ok) {
 #pragma unroll
               for (int i = 0; i < 32; i += 8)

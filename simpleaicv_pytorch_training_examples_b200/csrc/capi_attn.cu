@@ -67,12 +67,12 @@ bool encode_4d(CUtensorMap* m, const void* ptr, int D, int L, int H, int B, cons
   return true;
 }
 
+// persistent grid: MINB (1 or 2) CTAs per SM; the kernels are compiled with __launch_bounds__(192, MINB) and
+// their shared-memory / TMEM footprints were sized for exactly that residency
 template <typename K>
-int persistent_grid(K kernel, int smem, long long total) {
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kAttnThreads, smem) != cudaSuccess || occ < 1) occ = 1;
-  if (occ > 2) occ = 2;
-  const long long g = (long long)g_sms * occ;
+int persistent_grid(K kernel, int minb, long long total) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  const long long g = (long long)g_sms * minb;
   return (int)(total < g ? total : g);
 }
 
@@ -106,7 +106,7 @@ int launch_fwd(const saicv_attn_args* a, cudaStream_t st) {
   cudaGetSymbolAddress(&flag, g_attn_error);
   p.error_flag = reinterpret_cast<int*>(flag);
   const long long total = (long long)a->b * a->h * p.num_q_tiles;
-  const int grid = persistent_grid(kernel, Cfg::kSmemBytes, total);
+  const int grid = persistent_grid(kernel, MINB, total);
   kernel<<<grid, kAttnThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, p);
   return check_launch("attn_fwd_sm100_kernel");
 }
@@ -158,7 +158,7 @@ int launch_bwd_phase(const saicv_attn_bwd_args* a, cudaStream_t st) {
   cudaGetSymbolAddress(&flag, g_attn_error);
   p.error_flag = reinterpret_cast<int*>(flag);
   const long long total = (long long)f->b * f->h * p.num_tiles;
-  const int grid = persistent_grid(kernel, Cfg::kSmemBytes, total);
+  const int grid = persistent_grid(kernel, MINB, total);
   kernel<<<grid, kAttnThreads, Cfg::kSmemBytes, st>>>(r0, r1, c0, c1, p);
   return check_launch("attn_bwd_sm100_kernel");
 }
@@ -203,7 +203,7 @@ int bwd_for(const saicv_attn_bwd_args* a, cudaStream_t st) {
   return launch_bwd_phase<DQK, DV, true, tB, twoB ? 2 : 1>(a, st);
 }
 
-#define SAICV_ATTN_SHAPES(X) X(32, 32) X(64, 64) X(80, 80) X(96, 64) X(112, 80) X(192, 64) X(208, 80)
+#define SAICV_ATTN_SHAPES(X) X(32, 32) X(64, 64) X(80, 80) X(96, 64) X(112, 64) X(112, 80) X(128, 80) X(192, 64) X(208, 80)
 
 }  // namespace
 
@@ -218,6 +218,7 @@ int saicv_attn_error(void) {
 int saicv_attn_fwd(const saicv_attn_args* a, void* stream) {
   if (!ensure()) return 1;
   if (a->lq < 1 || a->lk < 1 || a->b < 1 || a->h < 1) return set_error("saicv_attn_fwd: empty problem");
+  if (!(a->scale > 0.f)) return set_error("saicv_attn_fwd: the softmax scale must be positive");
   if (a->key_mask_bits && a->mask_words * 32 < ((a->lk + 127) / 128) * 128)
     return set_error("saicv_attn_fwd: mask_words must cover lk rounded up to 128 keys");
 #define X(Q, V) if (a->dqk == Q && a->dv == V) return fwd_for<Q, V>(a, (cudaStream_t)stream);

@@ -534,3 +534,48 @@ def col2im_nhwc(dcols, n, h, w, c, k, stride, pad):
     dx = torch.empty(n, h, w, c, device=dcols.device, dtype=torch.bfloat16)
     _lib.call('saicv_col2im_nhwc', _p(dcols), _p(dx), n, h, w, c, k, stride, pad, _stream())
     return dx
+
+
+# ----------------------------------------------------------------------------- SAM image encoder kernels
+def window_partition(x, ws):
+    """x bf16 [B, H, W, C] -> (windows [B*nW, ws*ws, C], (nwy, nwx)); padding tokens are zero."""
+    b, h, w, c = x.shape
+    nwy, nwx = (h + ws - 1) // ws, (w + ws - 1) // ws
+    out = torch.empty(b * nwy * nwx, ws * ws, c, device=x.device, dtype=torch.bfloat16)
+    _lib.call('saicv_window_partition', _p(x), _p(out), b, h, w, c, ws, _stream())
+    return out, (nwy, nwx)
+
+
+def window_unpartition(windows, b, h, w, ws):
+    c = windows.shape[-1]
+    out = torch.empty(b, h, w, c, device=windows.device, dtype=torch.bfloat16)
+    _lib.call('saicv_window_unpartition', _p(windows), _p(out), b, h, w, c, ws, _stream())
+    return out
+
+
+def add_pos_embed(x, pos):
+    """x fp32 [B, ...] += pos fp32 [...] in place."""
+    _lib.call('saicv_add_pos_embed', _p(x), _p(pos), x.shape[0], pos.numel(), _stream())
+    return x
+
+
+def relpos_dqk(hd, sh, sw):
+    return (hd + sh + sw + 15) // 16 * 16
+
+
+def relpos_build(qkv, rel_pos_h, rel_pos_w, bw, heads, hd, sh, sw, scale):
+    """qkv bf16 [bw, sh*sw, 3*heads*hd] -> (qe, ke) bf16 [bw, heads, sh*sw, dqk] for attn_fwd(scale=1)."""
+    dqk = relpos_dqk(hd, sh, sw)
+    qe = torch.empty(bw, heads, sh * sw, dqk, device=qkv.device, dtype=torch.bfloat16)
+    ke = torch.empty_like(qe)
+    _lib.call('saicv_relpos_build', _p(qkv), _p(rel_pos_h), _p(rel_pos_w), _p(qe), _p(ke), bw, heads, hd, sh, sw, dqk, scale, _stream())
+    return qe, ke
+
+
+def relpos_bwd(dqe, qkv, rel_pos_h, rel_pos_w, dqkv, d_rel_pos_h, d_rel_pos_w, bw, heads, hd, sh, sw, scale, accumulate=False):
+    dqk = dqe.shape[-1]
+    rows = bw * heads * sh * sw
+    nblk = _lib.load().saicv_relpos_bwd_blocks(rows)
+    partial = torch.empty((nblk + 1) * (2 * sh - 1 + 2 * sw - 1) * hd, device=dqe.device, dtype=torch.float32)
+    _lib.call('saicv_relpos_bwd', _p(dqe), _p(qkv), _p(rel_pos_h), _p(rel_pos_w), _p(dqkv), _p(partial), _p(d_rel_pos_h),
+              _p(d_rel_pos_w), bw, heads, hd, sh, sw, dqk, scale, int(accumulate), _stream())

@@ -29,7 +29,24 @@ CASES = [
     ('darknettiny_c10_b2_64px', 'darknet', 'darknettiny', {}, 10, (2, 3, 64, 64), 2, True),
     ('van_b0_c10_b2_64px', 'van', 'van_b0', {}, 10, (2, 3, 64, 64), 6, True),
     ('van_b1_c10_b1_64px', 'van', 'van_b1', {}, 10, (1, 3, 64, 64), 7, True),
+    # SAM ViT image encoder (windowed 14x14 blocks with padding 20 -> 28, one global block, rel-pos tables and pos_embed
+    # randomised with seed 100 + seed so that they matter); num_classes unused; loss = mean(out * proj)
+    ('sam_enc_e128_h2_b3_320px', 'sam', 'ViTImageEncoder',
+     {'image_size': 320, 'patch_size': 16, 'embedding_planes': 128, 'block_nums': 3, 'head_nums': 2, 'out_planes': 256,
+      'window_size': 14, 'global_attn_indexes': (1,)}, 0, (1, 3, 320, 320), 8, False),
 ]
+
+
+def sam_randomize(tensors, seed):
+    """Deterministic non-zero values for the zero-initialised pos_embed / rel_pos tables (dict name -> tensor, in place)."""
+    g = torch.Generator().manual_seed(100 + seed)
+    for n in sorted(tensors):
+        if 'rel_pos' in n or n == 'pos_embed':
+            tensors[n].copy_(torch.randn(tensors[n].shape, generator=g) * 0.2)
+
+
+def sam_proj(shape, out_planes, grid, seed):
+    return torch.randn(shape[0], out_planes, grid, grid, generator=torch.Generator().manual_seed(500 + seed))
 
 
 def oracle_init(family, arch, kwargs, nc, seed):
@@ -46,6 +63,12 @@ def oracle_init(family, arch, kwargs, nc, seed):
     if family == 'van':
         from oracle import van
         return van.init_state(arch, nc, seed)
+    if family == 'sam':
+        from oracle import sam_encoder
+        k = kwargs
+        sd = sam_encoder.init_state(seed, k['image_size'], k['patch_size'], k['embedding_planes'], k['block_nums'], k['head_nums'], 4,
+                                    k['out_planes'], k['window_size'], k['global_attn_indexes'])
+        return sd
     raise KeyError(family)
 
 
@@ -72,6 +95,12 @@ def oracle_run(family, arch, kwargs, sd, x, y, training=True):
         if training:
             return van.loss_and_grads(sd, x, y, arch)
         return van.forward(sd, x, arch, training=False)
+    if family == 'sam':
+        from oracle import sam_encoder
+        k = kwargs
+        if training:
+            return sam_encoder.loss_and_grads(sd, x, y, k['head_nums'], k['window_size'], k['global_attn_indexes'], k['patch_size'])
+        return sam_encoder.forward(sd, x, k['head_nums'], k['window_size'], k['global_attn_indexes'], k['patch_size'])
     raise KeyError(family)
 
 
@@ -96,14 +125,25 @@ def main():
             print(tag, 'skipped (oracle not available yet):', e)
             continue
         torch.manual_seed(seed)
-        model = backbones.__dict__[arch](num_classes=nc, **kwargs)
+        if family == 'sam':
+            enc = ref_import.module('SimpleAICV.interactive_segmentation.models.segment_anything.image_encoder')
+            model = enc.ViTImageEncoder(**kwargs)
+        else:
+            model = backbones.__dict__[arch](num_classes=nc, **kwargs)
         sd0 = {k: v.clone() for k, v in model.state_dict().items()}
         assert list(sd0.keys()) == list(osd.keys()), 'oracle state_dict keys != reference'
         assert all(torch.equal(sd0[k], osd[k]) for k in sd0), 'oracle init != reference init'
-        x, y = make_input(shape, nc, seed)
+        x, y = make_input(shape, max(nc, 1), seed)
         model.train()
-        logits = model(x)
-        loss = CELoss()(logits, y)
+        if family == 'sam':
+            with torch.no_grad():
+                sam_randomize(dict(model.named_parameters()), seed)
+            y = sam_proj(shape, kwargs['out_planes'], kwargs['image_size'] // kwargs['patch_size'], seed)
+            logits = model(x)
+            loss = (logits.float() * y).mean()
+        else:
+            logits = model(x)
+            loss = CELoss()(logits, y)
         loss.backward()
         fix = {
             'family': family, 'arch': arch, 'kwargs': kwargs, 'num_classes': nc, 'seed': seed, 'shape': shape, 'y': y,

@@ -21,7 +21,7 @@ def load_fixture(path):
     fix.setdefault('family', 'resnet')
     fix.setdefault('kwargs', {})
     if 'x' not in fix:  # larger inputs are regenerated from the seed and checked against a digest
-        x, _ = make_golden.make_input(tuple(fix['shape']), fix['num_classes'], fix['seed'])
+        x, _ = make_golden.make_input(tuple(fix['shape']), max(fix['num_classes'], 1), fix['seed'])
         assert abs(float(x.double().sum()) - fix['x_digest'][0]) < 1e-6 and torch.equal(x.flatten()[:4], fix['x_digest'][1])
         fix['x'] = x
     return fix
@@ -33,6 +33,8 @@ def test_oracle_reproduces_reference_outputs(path):
     torch.set_num_threads(1)
     fam, arch, kw = fix['family'], fix['arch'], fix['kwargs']
     sd = make_golden.oracle_init(fam, arch, kw, fix['num_classes'], fix['seed'])
+    if fam == 'sam':
+        make_golden.sam_randomize(sd, fix['seed'])
     logits, loss, grads = make_golden.oracle_run(fam, arch, kw, sd, fix['x'], fix['y'])
     # fp32 vs fp32 on CPU: rtol 1e-5; identical torch builds give bit equality
     torch.testing.assert_close(logits, fix['logits'], rtol=1e-5, atol=1e-5)
@@ -52,4 +54,4 @@ def test_oracle_reproduces_reference_outputs(path):
 
 def test_golden_fixtures_cover_every_built_family():
     fams = {load_fixture(p)['family'] for p in GOLDEN}
-    assert {'resnet', 'vit', 'darknet', 'van'} <= fams, fams
+    assert {'resnet', 'vit', 'darknet', 'van', 'sam'} <= fams, fams

@@ -141,3 +141,38 @@ def test_van_oracle_and_constructor_match_reference(arch):
     for n, p in ref.named_parameters():
         rel = ((gr[n] - p.grad).norm() / p.grad.norm().clamp_min(1e-20)).item()
         assert rel < 1e-4 or (gr[n] - p.grad).abs().max().item() < 1e-7, (n, rel)
+
+
+def test_sam_encoder_oracle_and_constructor_match_reference():
+    """oracle/sam_encoder.py and the B200 ViTImageEncoder shell vs segment_anything/image_encoder.py:259-331
+    (windowed blocks with padding + a global block; pos_embed / rel-pos tables randomised)."""
+    from oracle import sam_encoder as se
+    from simpleaicv_pytorch_training_examples_b200.interactive_segmentation.models.segment_anything import image_encoder as mine
+    ref = ref_import.module('SimpleAICV.interactive_segmentation.models.segment_anything.image_encoder')
+    kw = dict(image_size=160, patch_size=16, embedding_planes=128, block_nums=2, head_nums=2, out_planes=256, window_size=7,
+              global_attn_indexes=(1,))
+    torch.manual_seed(3)
+    r = ref.ViTImageEncoder(**kw)
+    torch.manual_seed(3)
+    m = mine.ViTImageEncoder(**kw)
+    sd = se.init_state(3, 160, 16, 128, 2, 2, 4, 256, 7, (1,))
+    rs, ms = r.state_dict(), m.state_dict()
+    assert list(rs.keys()) == list(ms.keys()) == list(sd.keys())
+    assert all(torch.equal(rs[k], ms[k]) and torch.equal(rs[k], sd[k]) for k in rs)
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for n, p in r.named_parameters():
+            if 'rel_pos' in n or n == 'pos_embed':
+                v = torch.randn(p.shape, generator=g) * 0.2
+                p.copy_(v)
+                sd[n].copy_(v)
+    x = torch.randn(2, 3, 160, 160, generator=g)
+    proj = torch.randn(2, 256, 10, 10, generator=g)
+    r.train()
+    out = r(x)
+    (out.float() * proj).mean().backward()
+    o, _, gr = se.loss_and_grads(sd, x, proj, 2, 7, (1,))
+    torch.testing.assert_close(o, out.detach(), rtol=1e-4, atol=1e-4)
+    for n, p in r.named_parameters():
+        rel = ((gr[n] - p.grad).norm() / p.grad.norm().clamp_min(1e-20)).item()
+        assert rel < 1e-4, (n, rel)
