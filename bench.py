@@ -95,11 +95,12 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def vit_optimizer_cfg(model):
+def vit_optimizer_cfg(model, capturable=False):
     class _Cfg:
         optimizer = ('AdamW', {'lr': 5e-4, 'global_weight_decay': False, 'weight_decay': 0.05,
                                'no_weight_decay_layer_name_list': ['position_encoding', 'cls_token'],
-                               'lr_layer_decay': 0.65, 'lr_layer_decay_block': model.blocks, 'block_name': 'blocks'})
+                               'lr_layer_decay': 0.65, 'lr_layer_decay_block': model.blocks, 'block_name': 'blocks',
+                               'capturable': capturable})
     return _Cfg
 
 
@@ -388,7 +389,7 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
     else:
         model = backbones.vit_base_patch16(image_size=224, num_classes=1000, drop_path_prob=0.1, global_pool=True).to(dev).train()
         crit = losses.OneHotLabelCELoss().to(dev)
-        opt, _ = tutils.build_optimizer(vit_optimizer_cfg(model), model)
+        opt, _ = tutils.build_optimizer(vit_optimizer_cfg(model, capturable=(world == 1)), model)
     net = B200DataParallel(model) if world > 1 else model
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
@@ -444,10 +445,25 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
     # end to end through the public API: every step's batch comes from pinned host memory through
     # tools.utils.CudaPrefetcher (the loader wrapper train_classification uses: H2D of batch i+1 on a
     # side stream while step i computes) and the loss is read back to the host every step
+    # At N = 1 the step is replayed from ONE CUDA graph (graph.GraphedTrainStep, part of the package's API): the host
+    # reads every step's loss, so without the graph the ~600 C-ABI launches of the next step could not be issued ahead.
+    graphed, graph_note = None, 'eager (N > 1: NCCL work is issued from autograd hooks)'
+    if world == 1 and not args.no_graph:
+        try:
+            from simpleaicv_pytorch_training_examples_b200.graph import GraphedTrainStep
+            graphed = GraphedTrainStep(net, crit, opt, x_dev, y_dev)
+            graph_note = 'one CUDA graph per step (graph.GraphedTrainStep)'
+        except Exception as e:  # pragma: no cover
+            graphed, graph_note = None, f'eager (graph capture failed: {type(e).__name__}: {e})'
+            torch.cuda.synchronize()
+
     def e2e_loop(k):
         host_batches = ({'image': x_host, 'label': y_host} for _ in range(k))
         for batch in tutils.CudaPrefetcher(host_batches, dev):
-            step(batch['image'], batch['label']).item()
+            if graphed is not None:
+                graphed(batch['image'], batch['label']).item()
+            else:
+                step(batch['image'], batch['label']).item()
 
     e2e_loop(2)
     e2e_ms = timed(lambda: e2e_loop(args.steps), 1) / args.steps
@@ -472,7 +488,7 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
         rec = {'metric': METRICS[model_name], 'value': value, 'unit': 'images/s', 'ms_per_step': ms_step,
                'e2e': {'value': B * world / (e2e_ms / 1e3), 'unit': 'images/s', 'ms_per_step': e2e_ms,
                        'h2d_bytes_per_step': (x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()) * world,
-                       'd2h_bytes_per_step': 4 * world},
+                       'd2h_bytes_per_step': 4 * world, 'mode': graph_note},
                'gpu_launches': int(launches), 'roofline': roof, 'clocks': clocks, 'workload': WORKLOADS[model_name],
                'ddp_check': ddp_check}
     del model, net, opt
@@ -530,6 +546,7 @@ def main():
     ap.add_argument('--dump-ops', default=None, help='write the per-op timing table (csv) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-second-model', action='store_true', help='skip the sub-record of the other BASELINE model')
+    ap.add_argument('--no-graph', action='store_true', help='end-to-end loop without the CUDA graph (eager launches)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

@@ -201,34 +201,26 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, BN, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, DV, 0, 1);
-      uint32_t it = 0, gs = 0, gp = 0;   // work items, score blocks issued, P V blocks issued (per-CTA stream counters)
-      // S for block j of the current item: only needs K_j and the softmax warps to have COPIED S_{j-1} out of TMEM, so it
-      // is issued ahead of P_{j-1} V_{j-1} and runs on the tensor core while the exponentials of block j-1 are computed.
-      auto issue_s = [&](int j) {
-        const int st = gs % kStages;
-        const uint32_t ph = (gs / kStages) & 1;
-        const int nj = (min(BN, p.Lk - j * BN) + 15) & ~15;
-        mbar_wait(&k_full[st], ph);
-        mbar_wait(s_empty, (gs & 1) ^ 1);
-        tc_fence_after();
-        issue_scores<DQK>(tmem_S, smem_u32(sQ), 16384, smem_u32(sK + st * Cfg::KBYTES), BN * 128, idesc_with_n(idesc_s, nj));
-        umma_commit(&k_empty[st]);
-        umma_commit(s_full);
-        if (j == nkb - 1) umma_commit(q_empty);
-        ++gs;
-      };
+      uint32_t it = 0, g = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
         mbar_wait(q_full, it & 1);
-        issue_s(0);
-        for (int j = 0; j < nkb; ++j, ++gp) {
-          if (j + 1 < nkb) issue_s(j + 1);
+        for (int j = 0; j < nkb; ++j, ++g) {
+          const int st = g % kStages;
+          const uint32_t ph = (g / kStages) & 1;
+          const int nvalid = min(BN, p.Lk - j * BN);
+          const int nj = (nvalid + 15) & ~15;
+          // ---- S_j = Q K_j^T
+          mbar_wait(&k_full[st], ph);
+          mbar_wait(s_empty, (g & 1) ^ 1);
+          tc_fence_after();
+          issue_scores<DQK>(tmem_S, smem_u32(sQ), 16384, smem_u32(sK + st * Cfg::KBYTES), BN * 128, idesc_with_n(idesc_s, nj));
+          umma_commit(&k_empty[st]);
+          umma_commit(s_full);
+          if (j == nkb - 1) umma_commit(q_empty);
           // ---- O (+)= P_j V_j
-          const int st = gp % kStages;
-          const uint32_t ph = (gp / kStages) & 1;
-          const int nj = (min(BN, p.Lk - j * BN) + 15) & ~15;
           mbar_wait(&v_full[st], ph);
           if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);   // the previous item's O has been read out
-          mbar_wait(p_full, gp & 1);
+          mbar_wait(p_full, g & 1);
           tc_fence_after();
           issue_pv(tmem_O, smem_u32(sP), smem_u32(sV + st * Cfg::VBYTES), BN * 128, nj, idesc_o, j > 0);
           umma_commit(&v_empty[st]);
@@ -260,55 +252,64 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           return dead;
         };
         mbar_wait(s_full, g & 1);
+        if (g > 0) mbar_wait(pv_done, (g - 1) & 1);   // P_{g-1} V_{g-1} no longer reads the P tile (and O is quiescent)
         tc_fence_after();
-        // All of S_j goes to registers with ONE wait (TMEM load latency is paid once per block); the TMEM S buffer is
-        // handed back at once, so the tensor core computes S_{j+1} while this block's exponentials are evaluated.
-        uint32_t v[4][32];
+        // Single pass over S_j.  The block is processed optimistically with the current reference; if some chunk
+        // exceeds it by more than 2^8 the reference is raised (O in TMEM is rescaled, warp-collectively) and, unless
+        // nothing of this block was written yet, the block is started over with the new reference.
+        // (Measured alternatives on B200, ViT-B shape: all of S in registers + S_{j+1} issued ahead of P_j V_j: 226 us;
+        //  8 softmax warps with a half-row max exchange: 228 us; this form: 179 us.)
+        bool restart;
+        float rs;
+        do {
+          restart = false;
+          rs = 0.f;
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_S + lane_off + c * 32, v);
+            tmem_ld_wait();
+            const uint32_t dead = dead_bits(c);
+            const float cm = chunk_max(v, dead, -INFINITY);
+            const bool raise = cm > m_ref + thr_raw;           // (-inf + thr == -inf: the first valid score always raises)
+            if (__any_sync(0xffffffffu, raise)) {
+              float bm = cm;                                   // maximum of chunks c .. end of this block
+              for (int c2 = c + 1; c2 < nchunks; ++c2) {
+                uint32_t t[32];
+                tmem_ld_32x32(tmem_S + lane_off + c2 * 32, t);
+                tmem_ld_wait();
+                bm = chunk_max(t, dead_bits(c2), bm);
+              }
+              const bool had_ref = m_ref != -INFINITY;
+              const float m_new = raise ? bm : m_ref;
+              const float corr = (raise && had_ref) ? ex2_approx((m_ref - m_new) * p.scale_log2) : 1.f;
+              l *= corr;
+              if (j > 0 && __any_sync(0xffffffffu, raise && had_ref)) {   // blocks < j sit in TMEM relative to the old reference
+#pragma unroll 1
+                for (int c2 = 0; c2 < OCOLS / 32; ++c2) {
+                  uint32_t t[32];
+                  tmem_ld_32x32(tmem_O + lane_off + c2 * 32, t);
+                  tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < nchunks) tmem_ld_32x32(tmem_S + lane_off + c * 32, v[c]);
-        tmem_ld_wait();
+                  for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * corr);
+                  tmem_st_32x32(tmem_O + lane_off + c2 * 32, t);
+                }
+                tmem_st_wait();
+              }
+              m_ref = m_new;
+              if (c > 0) {   // chunks 0 .. c-1 were written relative to the old reference
+                restart = true;
+                break;
+              }
+            }
+            const float msl = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
+            rs = chunk_exp_store(v, dead, p.scale_log2, msl, rs, prow + (c >> 1) * 16384, (c & 1) * 4, sw);
+          }
+        } while (restart);
+        l += rs;
+        // S fully consumed: the MMA warp may overwrite it with the next block's scores
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);
-        uint32_t dead[4];
-        float bm = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < nchunks) {
-            dead[c] = dead_bits(c);
-            bm = chunk_max(v[c], dead[c], bm);
-          }
-        // P_{g-1} V_{g-1} must have finished before the P tile is overwritten (and before O is touched below)
-        if (g > 0) mbar_wait(pv_done, (g - 1) & 1);
-        tc_fence_after();
-        // lazy reference: raise it only when this block exceeds it by more than 2^8 (always on the first valid score)
-        const bool raise = bm > m_ref + thr_raw;
-        if (__any_sync(0xffffffffu, raise)) {
-          const bool had_ref = m_ref != -INFINITY;
-          const float corr = (raise && had_ref) ? ex2_approx((m_ref - bm) * p.scale_log2) : 1.f;
-          l *= corr;
-          if (j > 0 && __any_sync(0xffffffffu, raise && had_ref)) {   // blocks < j sit in TMEM relative to the old reference
-#pragma unroll 1
-            for (int c2 = 0; c2 < OCOLS / 32; ++c2) {
-              uint32_t t[32];
-              tmem_ld_32x32(tmem_O + lane_off + c2 * 32, t);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * corr);
-              tmem_st_32x32(tmem_O + lane_off + c2 * 32, t);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-          }
-          if (raise) m_ref = bm;
-        }
-        const float msl = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
-        float rs = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < nchunks) rs = chunk_exp_store(v[c], dead[c], p.scale_log2, msl, rs, prow + (c >> 1) * 16384, (c & 1) * 4, sw);
-        l += rs;
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);

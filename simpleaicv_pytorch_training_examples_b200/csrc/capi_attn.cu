@@ -68,10 +68,24 @@ bool encode_4d(CUtensorMap* m, const void* ptr, int D, int L, int H, int B, cons
 }
 
 // persistent grid: MINB (1 or 2) CTAs per SM; the kernels are compiled with __launch_bounds__(192, MINB) and
-// their shared-memory / TMEM footprints were sized for exactly that residency
+// their shared-memory / TMEM footprints were sized for exactly that residency (320 threads: 2 x 102 registers)
+int* error_flag_ptr() {   // resolved once (not during a later CUDA-graph capture)
+  static int* ptr = nullptr;
+  if (!ptr) {
+    void* f = nullptr;
+    cudaGetSymbolAddress(&f, g_attn_error);
+    ptr = reinterpret_cast<int*>(f);
+  }
+  return ptr;
+}
+
 template <typename K>
 int persistent_grid(K kernel, int minb, long long total) {
-  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  static bool carve = false;
+  if (!carve) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carve = true;
+  }
   const long long g = (long long)g_sms * minb;
   return (int)(total < g ? total : g);
 }
@@ -102,9 +116,7 @@ int launch_fwd(const saicv_attn_args* a, cudaStream_t st) {
   p.o_sb = a->o_strides[0]; p.o_sh = a->o_strides[1]; p.o_sl = a->o_strides[2];
   p.lse = a->lse;
   p.mask_bits = a->key_mask_bits; p.mask_words = a->mask_words;
-  void* flag = nullptr;
-  cudaGetSymbolAddress(&flag, g_attn_error);
-  p.error_flag = reinterpret_cast<int*>(flag);
+  p.error_flag = error_flag_ptr();
   const long long total = (long long)a->b * a->h * p.num_q_tiles;
   const int grid = persistent_grid(kernel, MINB, total);
   kernel<<<grid, kAttnThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, p);
@@ -154,9 +166,7 @@ int launch_bwd_phase(const saicv_attn_bwd_args* a, cudaStream_t st) {
     p.s1b = a->dv_strides[0]; p.s1h = a->dv_strides[1]; p.s1l = a->dv_strides[2];
   }
   p.dk_cols = a->dk_cols > 0 ? a->dk_cols : DQK;
-  void* flag = nullptr;
-  cudaGetSymbolAddress(&flag, g_attn_error);
-  p.error_flag = reinterpret_cast<int*>(flag);
+  p.error_flag = error_flag_ptr();
   const long long total = (long long)f->b * f->h * p.num_tiles;
   const int grid = persistent_grid(kernel, MINB, total);
   kernel<<<grid, kAttnThreads, Cfg::kSmemBytes, st>>>(r0, r1, c0, c1, p);

@@ -47,19 +47,22 @@ def _sam(**kwargs):
     return SAM(**kwargs)
 
 
+def _variant(defaults, image_size, patch_size, kwargs):
+    cfg = dict(image_size=image_size, patch_size=patch_size, prompt_encoder_embedding_planes=256, **defaults)
+    cfg.update(kwargs)
+    return _sam(**cfg)
+
+
 def sam_b(image_size=1024, patch_size=16, **kwargs):
-    return _sam(image_size=image_size, patch_size=patch_size, image_encoder_embedding_planes=768, image_encoder_block_nums=12,
-                image_encoder_head_nums=12, image_encoder_global_attn_indexes=[2, 5, 8, 11], prompt_encoder_embedding_planes=256,
-                **kwargs)
+    return _variant(dict(image_encoder_embedding_planes=768, image_encoder_block_nums=12, image_encoder_head_nums=12,
+                         image_encoder_global_attn_indexes=[2, 5, 8, 11]), image_size, patch_size, kwargs)
 
 
 def sam_l(image_size=1024, patch_size=16, **kwargs):
-    return _sam(image_size=image_size, patch_size=patch_size, image_encoder_embedding_planes=1024, image_encoder_block_nums=24,
-                image_encoder_head_nums=16, image_encoder_global_attn_indexes=[5, 11, 17, 23], prompt_encoder_embedding_planes=256,
-                **kwargs)
+    return _variant(dict(image_encoder_embedding_planes=1024, image_encoder_block_nums=24, image_encoder_head_nums=16,
+                         image_encoder_global_attn_indexes=[5, 11, 17, 23]), image_size, patch_size, kwargs)
 
 
 def sam_h(image_size=1024, patch_size=16, **kwargs):
-    return _sam(image_size=image_size, patch_size=patch_size, image_encoder_embedding_planes=1280, image_encoder_block_nums=32,
-                image_encoder_head_nums=16, image_encoder_global_attn_indexes=[7, 15, 23, 31], prompt_encoder_embedding_planes=256,
-                **kwargs)
+    return _variant(dict(image_encoder_embedding_planes=1280, image_encoder_block_nums=32, image_encoder_head_nums=16,
+                         image_encoder_global_attn_indexes=[7, 15, 23, 31]), image_size, patch_size, kwargs)

@@ -554,8 +554,9 @@ def window_unpartition(windows, b, h, w, ws):
 
 
 def add_pos_embed(x, pos):
-    """x fp32 [B, ...] += pos fp32 [...] in place."""
-    _lib.call('saicv_add_pos_embed', _p(x), _p(pos), x.shape[0], pos.numel(), _stream())
+    """x fp32 (any shape holding B copies of pos' extent) += pos fp32, broadcast over the batch, in place."""
+    assert x.numel() % pos.numel() == 0
+    _lib.call('saicv_add_pos_embed', _p(x), _p(pos), x.numel() // pos.numel(), pos.numel(), _stream())
     return x
 
 

@@ -114,7 +114,7 @@ def build_optimizer(config, model):
                                     nesterov=opt.get('nesterov', False))
     else:
         optimizer = torch.optim.AdamW(param_groups, lr=opt['lr'], betas=(opt.get('beta1', 0.9), opt.get('beta2', 0.999)),
-                                      eps=opt.get('eps', 1e-8))
+                                      eps=opt.get('eps', 1e-8), capturable=bool(opt.get('capturable', False)))
     return optimizer, info
 
 
