@@ -29,11 +29,15 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 METRICS = {'resnet50': 'images/sec (ResNet-50 224x224 training step, whole job)',
-           'vit_base_patch16': 'images/sec (ViT-B/16 224x224 training step, whole job)'}
+           'vit_base_patch16': 'images/sec (ViT-B/16 224x224 training step, whole job)',
+           'sam_h_encoder': 'images/sec (SAM ViT-H image encoder 1024x1024 training step, whole job)'}
 WORKLOADS = {'resnet50': 'ResNet-50 224x224 bs256/GPU training step (fwd+CELoss+bwd+grad all-reduce+SGD)',
-             'vit_base_patch16': 'ViT-B/16 224x224 bs256/GPU training step (fwd+OneHotLabelCELoss+bwd+grad all-reduce+AdamW)'}
-FWD_FLOPS = {'resnet50': 8.178e9, 'vit_base_patch16': 35.13e9}   # per image forward; a step is 3x
-ALGO_BYTES = {'resnet50': 130e6, 'vit_base_patch16': 3 * 65e6}  # per image per step, activations once each way (8d)
+             'vit_base_patch16': 'ViT-B/16 224x224 bs256/GPU training step (fwd+OneHotLabelCELoss+bwd+grad all-reduce+AdamW)',
+             'sam_h_encoder': ('SAM ViT-H image encoder 1024x1024 bs8/GPU training step (encoder fwd + feature MSE against a synthetic '
+                               'teacher map, the train_distill_sam_encoder step body + bwd + grad all-reduce + AdamW); prompt encoder / '
+                               'mask decoder are outside the built path')}
+FWD_FLOPS = {'resnet50': 8.178e9, 'vit_base_patch16': 35.13e9, 'sam_h_encoder': 5961e9}   # per image forward; a step is 3x
+ALGO_BYTES = {'resnet50': 130e6, 'vit_base_patch16': 3 * 65e6, 'sam_h_encoder': 3 * 3.1e9}  # per image per step, activations once each way (8d)
 
 
 def _peaks():
@@ -113,6 +117,10 @@ def r50_optimizer_cfg():
 
 def synthetic_batch(model_name, B, rank, pin):
     g = torch.Generator().manual_seed(1234 + rank)
+    if model_name == 'sam_h_encoder':   # student image + teacher feature map (train_distill_sam_encoder's tensors)
+        x = torch.randn(B, 3, 1024, 1024, generator=g)
+        y = torch.randn(B, 256, 64, 64, generator=g)
+        return (x.pin_memory(), y.pin_memory()) if pin else (x, y)
     x = torch.randn(B, 3, 224, 224, generator=g)
     if model_name == 'resnet50':
         y = torch.randint(0, 1000, (B,), generator=g)
@@ -306,6 +314,15 @@ def describe(name, a):
         mult = 2 if name.endswith('fwd') else 5                  # QK^T, PV | + dP, dQ, dK, dV (S recomputed)
         io = (4 if name.endswith('fwd') else 9) * b * l * h * d * 2
         return f'{name[6:]} B{b} L{l} H{h} D{d}', mult * 2.0 * b * h * l * l * d, float(io)
+    if name in ('saicv_attn_fwd', 'saicv_attn_bwd'):             # (byref(args struct), stream)
+        st = a[0]._obj
+        f = st if name.endswith('fwd') else st.fwd
+        bh = f.b * f.h
+        # algorithmic work: forward scores + PV; backward S (recomputed), dP, dQ, dK, dV once each (the two-phase
+        # kernel recomputes S and dP a second time; that is overhead, not counted)
+        macs = bh * f.lq * f.lk * ((f.dqk + f.dv) if name.endswith('fwd') else (3 * f.dqk + 2 * f.dv))
+        io = bh * 2 * ((f.lq * (f.dqk + f.dv) + f.lk * (f.dqk + f.dv)) * (1 if name.endswith('fwd') else 3))
+        return f'{name[6:]} BH{bh} Lq{f.lq} Lk{f.lk} dqk{f.dqk} dv{f.dv}', 2.0 * macs, float(io)
     return name[6:], 0.0, 0.0
 
 
@@ -379,17 +396,26 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
     from simpleaicv_pytorch_training_examples_b200.distributed import B200DataParallel, overlap_self_check
     from simpleaicv_pytorch_training_examples_b200.tools import utils as tutils
     dev = torch.device('cuda', local_rank)
-    B = args.batch
+    B = args.batch if model_name != 'sam_h_encoder' else 8
     torch.manual_seed(0)
     x_host, y_host = synthetic_batch(model_name, B, rank, True)
-    if model_name == 'resnet50':
+    if model_name == 'sam_h_encoder':
+        from simpleaicv_pytorch_training_examples_b200.interactive_segmentation.models.segment_anything import sam
+        model = sam.sam_h(image_size=1024, use_gradient_checkpoint=False).image_encoder.to(dev).train()
+        crit = torch.nn.MSELoss().to(dev)
+
+        class _Cfg:
+            optimizer = ('AdamW', {'lr': 1e-4, 'global_weight_decay': False, 'weight_decay': 0.05,
+                                   'no_weight_decay_layer_name_list': [], 'capturable': world == 1 or args.graph_ddp})
+        opt, _ = tutils.build_optimizer(_Cfg, model)
+    elif model_name == 'resnet50':
         model = backbones.resnet50(num_classes=1000).to(dev).train()
         crit = losses.CELoss().to(dev)
         opt, _ = tutils.build_optimizer(r50_optimizer_cfg(), model)
     else:
         model = backbones.vit_base_patch16(image_size=224, num_classes=1000, drop_path_prob=0.1, global_pool=True).to(dev).train()
         crit = losses.OneHotLabelCELoss().to(dev)
-        opt, _ = tutils.build_optimizer(vit_optimizer_cfg(model, capturable=(world == 1)), model)
+        opt, _ = tutils.build_optimizer(vit_optimizer_cfg(model, capturable=(world == 1 or args.graph_ddp)), model)
     net = B200DataParallel(model) if world > 1 else model
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
@@ -436,11 +462,11 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    steps = args.steps if model_name != 'sam_h_encoder' else max(3, args.steps // 3)
     l0 = _lib.launch_count()
-    ms_total = timed(lambda: step(x_dev, y_dev), args.steps)
-    launches = _lib.launch_count() - l0
-    ms_step = ms_total / args.steps
-    value = B * world / (ms_step / 1e3)
+    ms_total = timed(lambda: step(x_dev, y_dev), steps)
+    launches = (_lib.launch_count() - l0) * args.steps // steps
+    eager_ms_step = ms_total / steps
 
     # end to end through the public API: every step's batch comes from pinned host memory through
     # tools.utils.CudaPrefetcher (the loader wrapper train_classification uses: H2D of batch i+1 on a
@@ -448,14 +474,23 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
     # At N = 1 the step is replayed from ONE CUDA graph (graph.GraphedTrainStep, part of the package's API): the host
     # reads every step's loss, so without the graph the ~600 C-ABI launches of the next step could not be issued ahead.
     graphed, graph_note = None, 'eager (N > 1: NCCL work is issued from autograd hooks)'
-    if world == 1 and not args.no_graph:
+    if (world == 1 or args.graph_ddp) and not args.no_graph:
         try:
+            torch.cuda.empty_cache()
             from simpleaicv_pytorch_training_examples_b200.graph import GraphedTrainStep
             graphed = GraphedTrainStep(net, crit, opt, x_dev, y_dev)
-            graph_note = 'one CUDA graph per step (graph.GraphedTrainStep)'
+            graph_note = 'one CUDA graph per step (graph.GraphedTrainStep)' + (', NCCL bucket all-reduces captured' if world > 1 else '')
         except Exception as e:  # pragma: no cover
             graphed, graph_note = None, f'eager (graph capture failed: {type(e).__name__}: {e})'
             torch.cuda.synchronize()
+
+    # device-resident throughput: the same graph replayed on resident inputs when there is one, else the eager loop above
+    if graphed is not None:
+        graphed.replay()
+        ms_step = timed(graphed.replay, steps) / steps
+    else:
+        ms_step = eager_ms_step
+    value = B * world / (ms_step / 1e3)
 
     def e2e_loop(k):
         host_batches = ({'image': x_host, 'label': y_host} for _ in range(k))
@@ -466,7 +501,7 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
                 step(batch['image'], batch['label']).item()
 
     e2e_loop(2)
-    e2e_ms = timed(lambda: e2e_loop(args.steps), 1) / args.steps
+    e2e_ms = timed(lambda: e2e_loop(steps), 1) / steps
     clocks = sampler.stop() if rank == 0 else None
     rec = None
     if rank == 0:
@@ -484,13 +519,14 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
             d['calls'] //= 2
             d['flops'] /= 2
             d['bytes'] /= 2
-        roof = roofline_from_table(table, _peaks(), model_name, B, ms_step, dump_path)
+        roof = roofline_from_table(table, _peaks(), model_name, B, eager_ms_step, dump_path)
         rec = {'metric': METRICS[model_name], 'value': value, 'unit': 'images/s', 'ms_per_step': ms_step,
                'e2e': {'value': B * world / (e2e_ms / 1e3), 'unit': 'images/s', 'ms_per_step': e2e_ms,
                        'h2d_bytes_per_step': (x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()) * world,
                        'd2h_bytes_per_step': 4 * world, 'mode': graph_note},
                'gpu_launches': int(launches), 'roofline': roof, 'clocks': clocks, 'workload': WORKLOADS[model_name],
-               'ddp_check': ddp_check}
+               'ddp_check': ddp_check, 'eager_ms_per_step': eager_ms_step, 'per_gpu_batch': B, 'timed_steps': steps,
+               'value_mode': graph_note}
     del model, net, opt
     torch.cuda.empty_cache()
     return rec
@@ -506,6 +542,10 @@ def run_b200(args, rank, world, local_rank):
         second = 'vit_base_patch16' if args.model == 'resnet50' else 'resnet50'
         other = measure_model(second, args, rank, world, local_rank,
                               args.dump_ops.replace('.csv', f'_{second}.csv') if args.dump_ops else None)
+    sam_rec = None
+    if args.sam:
+        sam_rec = measure_model('sam_h_encoder', args, rank, world, local_rank,
+                                args.dump_ops.replace('.csv', '_sam_h_encoder.csv') if args.dump_ops else None)
     if rank != 0:
         return
     cpu_base = None
@@ -523,10 +563,16 @@ def run_b200(args, rank, world, local_rank):
     }
     if main.get('ddp_check'):
         line['ddp_check'] = main['ddp_check']
+    SUB = ('metric', 'value', 'unit', 'ms_per_step', 'eager_ms_per_step', 'value_mode', 'e2e', 'gpu_launches', 'roofline', 'clocks',
+           'workload', 'per_gpu_batch', 'timed_steps')
+    line['eager_ms_per_step'], line['value_mode'] = main['eager_ms_per_step'], main['value_mode']
     if other is not None:
         name = 'vit_base_patch16' if args.model == 'resnet50' else 'resnet50'
-        line[name] = {k: other[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'e2e', 'gpu_launches', 'roofline', 'clocks', 'workload')}
+        line[name] = {k: other[k] for k in SUB}
         line[name]['images_per_sec_per_gpu'] = other['value'] / world
+    if sam_rec is not None:
+        line['sam_h_encoder'] = {k: sam_rec[k] for k in SUB}
+        line['sam_h_encoder']['images_per_sec_per_gpu'] = sam_rec['value'] / world
     torch_base = os.path.join(ROOT, 'profiles', 'r02_torch_gpu_baseline.json')
     if os.path.exists(torch_base):
         line['torch_ddp_target'] = {'source': 'profiles/r02_torch_gpu_baseline.json (unmodified reference under torch DDP, same pool)',
@@ -546,6 +592,8 @@ def main():
     ap.add_argument('--dump-ops', default=None, help='write the per-op timing table (csv) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-second-model', action='store_true', help='skip the sub-record of the other BASELINE model')
+    ap.add_argument('--sam', action='store_true', help='add the SAM ViT-H image-encoder sub-record (BASELINE configs[3]: bs8, 1024x1024)')
+    ap.add_argument('--graph-ddp', action='store_true', help='N > 1: capture the step (NCCL all-reduces included) in one CUDA graph too')
     ap.add_argument('--no-graph', action='store_true', help='end-to-end loop without the CUDA graph (eager launches)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))

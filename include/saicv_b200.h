@@ -250,13 +250,14 @@ int saicv_add_pos_embed(float* x, const float* pos, int b, long long per_batch, 
  * [2sw-1][hd]; rows of qe / ke have dqk >= hd + sh + sw (multiple of 16) elements. */
 int saicv_relpos_build(const void* qkv, const float* rel_pos_h, const float* rel_pos_w, void* qe, void* ke,
                        int bw, int heads, int hd, int sh, int sw, int dqk, float scale, void* stream);
-/* Backward: dqe (gradient of qe from saicv_attn_bwd) -> dq into the q slot of dqkv (layout of qkv), and
- * d_rel_pos_h / d_rel_pos_w (+)=.  partial: fp32 workspace
- * (saicv_relpos_bwd_blocks(rows) + 1) * ((2sh-1) + (2sw-1)) * hd floats, rows = bw*heads*sh*sw. */
-int saicv_relpos_bwd_blocks(long long rows);
+/* Backward: dqe (gradient of qe from saicv_attn_bwd) -> dq into the q slot of dqkv (layout of qkv), plus the two
+ * operands of the table-gradient GEMM: ef bf16 [rows][nip] (the bias-column gradients re-indexed per row so that
+ * column idx is the rel_pos row it belongs to: height table in columns [0, 2sh-1), width table in
+ * [2sh-1, 2sh-1 + 2sw-1), zero padding up to nip, a multiple of 8) and qc bf16 [rows][hd] (the q rows, compact),
+ * rows = bw*heads*sh*sw.  [d_rel_pos_h ; d_rel_pos_w] = ef^T qc = saicv_linear_wgrad(ef, qc, M=rows, N=nip, K=hd). */
 int saicv_relpos_bwd(const void* dqe, const void* qkv, const float* rel_pos_h, const float* rel_pos_w,
-                     void* dqkv, float* partial, float* d_rel_pos_h, float* d_rel_pos_w, int bw, int heads,
-                     int hd, int sh, int sw, int dqk, float scale, int accumulate, void* stream);
+                     void* dqkv, void* ef, void* qc, int nip, int bw, int heads, int hd, int sh, int sw, int dqk,
+                     float scale, void* stream);
 
 /* ---- fused multi-head attention on tcgen05 / TMEM (csrc/attn_sm100.cuh) ------------------------------
  * Replaces the materialised attention of the reference: vit.py:62-80 (q k^T * scale, softmax, @ v),
@@ -279,6 +280,11 @@ typedef struct {
   int mask_words;
   int b, h, lq, lk, dqk, dv;
   float scale;
+  /* attention-probability dropout (nn.MultiheadAttention(dropout=p), detr.py:55-57): probability dropout_p of
+   * zeroing softmax(S)[q, k], survivors scaled by 1 / (1 - p); the mask is the counter hash of csrc/dropout_hash.cuh
+   * over (row (b*h + head)*lq + q, column k) under dropout_seed, recomputed by the backward.  0 = off. */
+  float dropout_p;
+  unsigned long long dropout_seed;
 } saicv_attn_args;
 int saicv_attn_fwd(const saicv_attn_args* a, void* stream);
 /* Backward: fwd holds the forward's arguments (out = the forward output, lse as written by it); dout has the
@@ -302,6 +308,35 @@ int saicv_attention_fwd(const void* qkv, void* out, float* lse, int b, int l, in
                         float scale, void* stream);
 int saicv_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                         float* delta, void* dqkv, int b, int l, int h, int d, float scale, void* stream);
+
+/* ---- DETR transformer glue (SimpleAICV/detection/models/detr.py:44-180; csrc/capi_detr.cu) -------------------
+ * Post-LayerNorm on the fp32 token stream: y = LN(z) (nullable), yb = bf16(y) (nullable),
+ * ypb = bf16(y + pos[row % pos_rows]) (nullable; pos fp32 [pos_rows][c]); stats fp32 [2][rows] (mean | rstd).
+ * c in {128, 256, 384, 512}. */
+int saicv_postln_fwd(const float* z, const float* gamma, const float* beta, float eps, float* y, void* yb,
+                     const float* pos, long long pos_rows, void* ypb, float* stats, long long rows, int c,
+                     void* stream);
+/* dz = LN'(dy) (+ dres), dy fp32: dz fp32 (nullable), dzb = bf16(dz) (nullable); dgamma / dbeta (+)= through the
+ * fp32 workspace partials [SAICV_BN_PARTIAL_ROWS][2*c] in a fixed order (bit-reproducible). */
+int saicv_postln_bwd(const float* dy, const float* z, const float* gamma, const float* stats, const float* dres,
+                     float* dz, void* dzb, float* partials, float* dgamma, float* dbeta, long long rows, int c,
+                     int accumulate, void* stream);
+/* xb = bf16(x) (nullable), xpb = bf16(x + pos[row % pos_rows]) (nullable); x fp32 [rows][c]. */
+int saicv_add_pos_cast(const float* x, const float* pos, long long pos_rows, void* xb, void* xpb, long long rows,
+                       int c, void* stream);
+/* Dropout with the counter hash of csrc/dropout_hash.cuh over the element index: out = keep ? in / (1 - p) : 0
+ * (+ resid, fp32, only with an fp32 out).  in / out are bf16 or fp32 (flags); the same call on a gradient with the
+ * same seed is the backward pass.  n %% 4 == 0. */
+int saicv_dropout(const void* in, int in_f32, const float* resid, void* out, int out_f32, long long n, float p,
+                  unsigned long long seed, void* stream);
+/* Per-head packing of projected rows into a score operand: dst bf16 [b][h][l][dp],
+ * dst[.., 0:hd] = src[(b*l + l') * ld + col0 + head*hd + :] * scale, dst[.., hd] = extra ? extra[b*l + l'] :
+ * extra_const (the column that carries nn.MultiheadAttention's additive float key_padding_mask against a constant-1
+ * column of the query operand), remaining columns 0.  unpack is the inverse on the leading hd columns. */
+int saicv_heads_pack(const void* src, int ld, int col0, const float* extra, float extra_const, void* dst, int b,
+                     int l, int h, int hd, int dp, float scale, void* stream);
+int saicv_heads_unpack(const void* src, void* dst, int ld, int col0, int b, int l, int h, int hd, int dp, float scale,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -152,17 +152,18 @@ def _keep(trace, key, t):
     return t
 
 
-def forward(sd, x, arch, training=True, emulate_bf16=False, trace=None):
-    """Logits of `arch` for the NCHW fp32 batch x; running statistics in `sd` are updated in
-    place when training (like nn.BatchNorm2d).  `trace` (a dict) receives the stage boundary
-    tensors: 'stem_out', 'pool_out', 'block{i}_out', 'logits'."""
+def features(sd, x, arch, training=True, emulate_bf16=False, trace=None, prefix=''):
+    """The convolutional body (stem, max pool, 4 stages) of `arch`: returns the last stage's output (C5 for the
+    ImageNet nets).  `prefix` is prepended to every state-dict key (DETR keeps the body under 'backbone.',
+    SimpleAICV/detection/models/backbones/detr_resnet.py:256-340 — same blocks as resnet.py)."""
     emu = emulate_bf16
     block, nums, cifar = ARCHS[arch]
     specs, _ = _cba_specs(arch)
     spec = {p: (k, s) for p, _, _, k, s in specs}
+    P = prefix
     if emu:
         x = x.bfloat16().float()
-    x = _keep(trace, 'stem_out', _act_store(F.relu(_conv_bn(sd, 'conv1', x, *spec['conv1'], training, emu)), emu))
+    x = _keep(trace, 'stem_out', _act_store(F.relu(_conv_bn(sd, P + 'conv1', x, *spec['conv1'], training, emu)), emu))
     if not cifar:
         x = _keep(trace, 'pool_out', F.max_pool2d(x, kernel_size=3, stride=2, padding=1))
     bidx = 0
@@ -173,14 +174,23 @@ def forward(sd, x, arch, training=True, emulate_bf16=False, trace=None):
             names = ['conv1', 'conv2'] + (['conv3'] if block == 'bottleneck' else [])
             for nm in names[:-1]:
                 k, s = spec[f'{p}.{nm}']
-                x = _act_store(F.relu(_conv_bn(sd, f'{p}.{nm}', x, k, s, training, emu)), emu)
+                x = _act_store(F.relu(_conv_bn(sd, f'{P}{p}.{nm}', x, k, s, training, emu)), emu)
             k, s = spec[f'{p}.{names[-1]}']
-            x = _conv_bn(sd, f'{p}.{names[-1]}', x, k, s, training, emu)       # no activation before the add
+            x = _conv_bn(sd, f'{P}{p}.{names[-1]}', x, k, s, training, emu)       # no activation before the add
             if f'{p}.downsample_conv' in spec:
                 k, s = spec[f'{p}.downsample_conv']
-                inp = _conv_bn(sd, f'{p}.downsample_conv', inp, k, s, training, emu)
+                inp = _conv_bn(sd, f'{P}{p}.downsample_conv', inp, k, s, training, emu)
             x = _keep(trace, f'block{bidx}_out', _act_store(F.relu(x + inp), emu))
             bidx += 1
+    return x
+
+
+def forward(sd, x, arch, training=True, emulate_bf16=False, trace=None):
+    """Logits of `arch` for the NCHW fp32 batch x; running statistics in `sd` are updated in
+    place when training (like nn.BatchNorm2d).  `trace` (a dict) receives the stage boundary
+    tensors: 'stem_out', 'pool_out', 'block{i}_out', 'logits'."""
+    emu = emulate_bf16
+    x = features(sd, x, arch, training, emu, trace)
     x = _act_store(F.adaptive_avg_pool2d(x, (1, 1)).flatten(1), emu)
     z = F.linear(x, _w_operand(sd['fc.weight'], emu))
     if emu:

@@ -19,13 +19,20 @@
 //   warps 2..5  softmax: thread = one query row (TMEM lane); tcgen05.ld S -> exp2 -> bf16 P into 128B-swizzled
 //               shared memory (the A operand of P V); O accumulated in registers with the online-softmax rescale
 #pragma once
+#include "dropout_hash.cuh"
 #include "ptx.cuh"
 
 namespace saicv {
 
 constexpr int kAttnThreads = 192;
 
+struct AttnDrop {            // attention-probability dropout (thresh == 0: off), see dropout_hash.cuh
+  uint32_t thresh, seed_lo, seed_hi;
+  float scale;                // 1 / (1 - p)
+};
+
 struct AttnParams {
+  AttnDrop drop;
   int B, H, Lq, Lk;
   int num_q_tiles;          // ceil(Lq / 128)
   float scale_log2;         // softmax scale * log2(e)
@@ -77,8 +84,10 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], uint32_t dea
 }
 // e = exp2(s * sl - msl) for one 32-column chunk (0 where dead), packed to bf16 into the 128B-swizzled A tile:
 // 16-byte pieces piece0 .. piece0+3 of this thread's 128-byte row (row & 7 == sw).  Returns rs + sum(e).
+template <bool DROP>
 __device__ __forceinline__ float chunk_exp_store(const uint32_t (&v)[32], uint32_t dead, float sl, float msl, float rs,
-                                                 uint8_t* row_base, int piece0, int sw) {
+                                                 uint8_t* row_base, int piece0, int sw, const AttnDrop& dr, uint32_t drow,
+                                                 uint32_t dcol0) {
 #pragma unroll
   for (int t = 0; t < 4; ++t) {   // 8 columns -> one 16-byte piece
     float e[8];
@@ -89,6 +98,11 @@ __device__ __forceinline__ float chunk_exp_store(const uint32_t (&v)[32], uint32
       for (int i = 0; i < 8; ++i) e[i] = ((dead >> (8 * t + i)) & 1u) ? 0.f : e[i];
     }
     rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+    if (DROP) {   // the row sum is that of the undropped probabilities; P V uses the dropped ones
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        e[i] = dropout_hash(dr.seed_lo, dr.seed_hi, drow, dcol0 + 8 * t + i) >= dr.thresh ? e[i] * dr.scale : 0.f;
+    }
     *reinterpret_cast<uint4*>(row_base + (((piece0 + t) ^ sw) << 4)) =
         make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
   }
@@ -110,7 +124,7 @@ struct AttnFwdCfg {
 // block's scores exceed it by more than 2^8 (lazy rescaling): O and the row sums then stay in TMEM across key
 // blocks (accumulating MMAs) and are read once per work item; a raise multiplies both by 2^((m_old - m_new) * scale_log2)
 // in TMEM (rare); the row sums live in registers and follow the same rescaling.
-template <int DQK, int DV, int MINB>
+template <int DQK, int DV, int MINB, bool DROP>
 __global__ void __launch_bounds__(kAttnThreads, MINB)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -302,7 +316,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
               }
             }
             const float msl = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
-            rs = chunk_exp_store(v, dead, p.scale_log2, msl, rs, prow + (c >> 1) * 16384, (c & 1) * 4, sw);
+            rs = chunk_exp_store<DROP>(v, dead, p.scale_log2, msl, rs, prow + (c >> 1) * 16384, (c & 1) * 4, sw, p.drop,
+                                 (uint32_t)(bh * p.Lq + qt * 128 + row), (uint32_t)(j * BN + c * 32));
           }
         } while (restart);
         l += rs;
@@ -349,6 +364,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 // ------------------------------------------------------------------------------------------------ backward
 struct AttnBwdParams {
+  AttnDrop drop;
   int B, H, Lq, Lk;
   int num_tiles;            // row tiles per (b, h): ceil(Lq / 128) in the dQ phase, ceil(Lk / 128) in the dK/dV phase
   float scale_log2, scale;
@@ -381,7 +397,7 @@ struct AttnBwdCfg {
   static constexpr int kSmemBytes = R0BYTES + R1BYTES + kStages * (C0BYTES + C1BYTES) + NA * ABYTES + 1024 /*lse, delta*/ + 256;
 };
 
-template <int DQK, int DV, bool ROWS_ARE_KEYS, int TMEM_COLS, int MINB>
+template <int DQK, int DV, bool ROWS_ARE_KEYS, int TMEM_COLS, int MINB, bool DROP>
 __global__ void __launch_bounds__(kAttnThreads, MINB)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                       const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1,
@@ -604,6 +620,22 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_con
               for (int i = 0; i < 8; ++i) {
                 pp[i] = ex2_approx(fmaf(__uint_as_float(sv[c][8 * t + i]), p.scale_log2, -lse_r));
                 ds[i] = pp[i] * (__uint_as_float(dv[c][8 * t + i]) - dl_r);
+              }
+            }
+            if (DROP) {
+              // A~ = M A / (1 - p):  dS = A (M dP / (1 - p) - D);  dV uses A~ (phase B's pp tile)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int col = j * BN + c * 32 + 8 * t + i;
+                const uint32_t qi = ROWS_ARE_KEYS ? (uint32_t)col : (uint32_t)grow;
+                const uint32_t ki = ROWS_ARE_KEYS ? (uint32_t)grow : (uint32_t)col;
+                const bool keep = dropout_hash(p.drop.seed_lo, p.drop.seed_hi, (uint32_t)bh * (uint32_t)p.Lq + qi, ki) >= p.drop.thresh;
+                const float dpv = keep ? __uint_as_float(dv[c][8 * t + i]) * p.drop.scale : 0.f;
+                float dlv;
+                if (ROWS_ARE_KEYS) dlv = sLse[64 + c * 32 + 8 * t + i];
+                else dlv = dl_r;
+                ds[i] = pp[i] * (dpv - dlv);
+                pp[i] = keep ? pp[i] * p.drop.scale : 0.f;
               }
             }
             if (dead != 0) {

@@ -90,10 +90,21 @@ int persistent_grid(K kernel, int minb, long long total) {
   return (int)(total < g ? total : g);
 }
 
-template <int DQK, int DV, int MINB>
+AttnDrop make_drop(const saicv_attn_args* a) {
+  AttnDrop d{};
+  if (a->dropout_p > 0.f) {
+    d.thresh = dropout_threshold(a->dropout_p);
+    d.seed_lo = (uint32_t)a->dropout_seed;
+    d.seed_hi = (uint32_t)(a->dropout_seed >> 32);
+    d.scale = 1.f / (1.f - a->dropout_p);
+  }
+  return d;
+}
+
+template <int DQK, int DV, int MINB, bool DROP>
 int launch_fwd(const saicv_attn_args* a, cudaStream_t st) {
   using Cfg = AttnFwdCfg<DQK, DV, MINB>;
-  auto kernel = attn_fwd_sm100_kernel<DQK, DV, MINB>;
+  auto kernel = attn_fwd_sm100_kernel<DQK, DV, MINB, DROP>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -116,6 +127,7 @@ int launch_fwd(const saicv_attn_args* a, cudaStream_t st) {
   p.o_sb = a->o_strides[0]; p.o_sh = a->o_strides[1]; p.o_sl = a->o_strides[2];
   p.lse = a->lse;
   p.mask_bits = a->key_mask_bits; p.mask_words = a->mask_words;
+  p.drop = make_drop(a);
   p.error_flag = error_flag_ptr();
   const long long total = (long long)a->b * a->h * p.num_q_tiles;
   const int grid = persistent_grid(kernel, MINB, total);
@@ -123,10 +135,10 @@ int launch_fwd(const saicv_attn_args* a, cudaStream_t st) {
   return check_launch("attn_fwd_sm100_kernel");
 }
 
-template <int DQK, int DV, bool KEYS, int TCOLS, int MINB>
+template <int DQK, int DV, bool KEYS, int TCOLS, int MINB, bool DROP>
 int launch_bwd_phase(const saicv_attn_bwd_args* a, cudaStream_t st) {
   using Cfg = AttnBwdCfg<DQK, DV, KEYS, TCOLS, MINB>;
-  auto kernel = attn_bwd_sm100_kernel<DQK, DV, KEYS, TCOLS, MINB>;
+  auto kernel = attn_bwd_sm100_kernel<DQK, DV, KEYS, TCOLS, MINB, DROP>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -156,6 +168,7 @@ int launch_bwd_phase(const saicv_attn_bwd_args* a, cudaStream_t st) {
   p.scale_log2 = f->scale * 1.4426950408889634f;
   p.lse = f->lse; p.delta = a->delta;
   p.mask_bits = f->key_mask_bits; p.mask_words = f->mask_words;
+  p.drop = make_drop(f);
   if (!KEYS) {
     p.d_out0 = reinterpret_cast<__nv_bfloat16*>(a->dq);
     p.s0b = a->dq_strides[0]; p.s0h = a->dq_strides[1]; p.s0l = a->dq_strides[2];
@@ -198,10 +211,19 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 }
 
 template <int DQK, int DV>
+constexpr bool kDropoutShape = (DQK == 32 && DV == 32) || (DQK == 48 && DV == 32) || (DQK == 64 && DV == 64);
+
+template <int DQK, int DV>
 int fwd_for(const saicv_attn_args* a, cudaStream_t st) {
   // two CTAs per SM whenever the tiles of both fit (hd <= 64 without bias columns)
   constexpr bool two = AttnFwdCfg<DQK, DV, 2>::kSmemBytes <= 115712;
-  return launch_fwd<DQK, DV, two ? 2 : 1>(a, st);
+  if (a->dropout_p > 0.f) {
+    // attention-probability dropout is compiled for the head sizes that train with it (DETR hd 32 with / without the
+    // key-bias column, ViT hd 64); the other shapes keep the mask-free instruction stream only
+    if constexpr (kDropoutShape<DQK, DV>) return launch_fwd<DQK, DV, two ? 2 : 1, true>(a, st);
+    else return set_error("attention dropout is not compiled for (score width, value width) = (%d, %d)", DQK, DV);
+  }
+  return launch_fwd<DQK, DV, two ? 2 : 1, false>(a, st);
 }
 template <int DQK, int DV>
 int bwd_for(const saicv_attn_bwd_args* a, cudaStream_t st) {
@@ -209,11 +231,19 @@ int bwd_for(const saicv_attn_bwd_args* a, cudaStream_t st) {
   constexpr int tA = colsA <= 256 ? 256 : 512, tB = colsB <= 256 ? 256 : 512;
   constexpr bool twoA = tA == 256 && AttnBwdCfg<DQK, DV, false, tA, 2>::kSmemBytes <= 115712;
   constexpr bool twoB = tB == 256 && AttnBwdCfg<DQK, DV, true, tB, 2>::kSmemBytes <= 115712;
-  if (int e = launch_bwd_phase<DQK, DV, false, tA, twoA ? 2 : 1>(a, st)) return e;
-  return launch_bwd_phase<DQK, DV, true, tB, twoB ? 2 : 1>(a, st);
+  if (a->fwd.dropout_p > 0.f) {
+    if constexpr (kDropoutShape<DQK, DV>) {
+      if (int e = launch_bwd_phase<DQK, DV, false, tA, twoA ? 2 : 1, true>(a, st)) return e;
+      return launch_bwd_phase<DQK, DV, true, tB, twoB ? 2 : 1, true>(a, st);
+    } else {
+      return set_error("attention dropout is not compiled for (score width, value width) = (%d, %d)", DQK, DV);
+    }
+  }
+  if (int e = launch_bwd_phase<DQK, DV, false, tA, twoA ? 2 : 1, false>(a, st)) return e;
+  return launch_bwd_phase<DQK, DV, true, tB, twoB ? 2 : 1, false>(a, st);
 }
 
-#define SAICV_ATTN_SHAPES(X) X(32, 32) X(64, 64) X(80, 80) X(96, 64) X(112, 64) X(112, 80) X(128, 80) X(192, 64) X(208, 80)
+#define SAICV_ATTN_SHAPES(X) X(32, 32) X(48, 32) X(64, 64) X(80, 80) X(96, 64) X(112, 64) X(112, 80) X(128, 80) X(192, 64) X(208, 80)
 
 }  // namespace
 
@@ -229,6 +259,7 @@ int saicv_attn_fwd(const saicv_attn_args* a, void* stream) {
   if (!ensure()) return 1;
   if (a->lq < 1 || a->lk < 1 || a->b < 1 || a->h < 1) return set_error("saicv_attn_fwd: empty problem");
   if (!(a->scale > 0.f)) return set_error("saicv_attn_fwd: the softmax scale must be positive");
+  if (!(a->dropout_p >= 0.f && a->dropout_p < 1.f)) return set_error("saicv_attn_fwd: dropout_p must be in [0, 1)");
   if (a->key_mask_bits && a->mask_words * 32 < ((a->lk + 127) / 128) * 128)
     return set_error("saicv_attn_fwd: mask_words must cover lk rounded up to 128 keys");
 #define X(Q, V) if (a->dqk == Q && a->dv == V) return fwd_for<Q, V>(a, (cudaStream_t)stream);

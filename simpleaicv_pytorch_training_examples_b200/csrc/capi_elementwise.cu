@@ -11,6 +11,7 @@
 
 #include "../../include/saicv_b200.h"
 #include "host_util.h"
+#include "vec8.cuh"
 
 namespace saicv {
 
@@ -38,29 +39,6 @@ namespace {
 
 constexpr int kThreads = 256;
 
-struct alignas(16) V8 {
-  __nv_bfloat162 h[4];
-};
-__device__ __forceinline__ void unpack8(const V8& v, float (&f)[8]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(v.h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ V8 pack8(const float (&f)[8]) {
-  V8 v;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v.h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return v;
-}
-__device__ __forceinline__ V8 ldg8(const void* p, long long vec_idx) {
-  return *(reinterpret_cast<const V8*>(p) + vec_idx);
-}
-__device__ __forceinline__ void stg8(void* p, long long vec_idx, const V8& v) {
-  *(reinterpret_cast<V8*>(p) + vec_idx) = v;
-}
 // act: 0 none, 1 ReLU, 2 LeakyReLU(0.1), 3 SiLU (darknet.py:16-31 ActivationBlock)
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == 3) return v * __fdividef(1.f, 1.f + __expf(-v));
@@ -604,8 +582,7 @@ __global__ void zero_upsample2_kernel(const void* __restrict__ dy, void* __restr
     const int h = (int)((pix / W) % H);
     const long long n = pix / ((long long)W * H);
     V8 val;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) val.h[k] = __floats2bfloat162_rn(0.f, 0.f);
+    val.q = make_uint4(0u, 0u, 0u, 0u);
     if (!(h & 1) && !(w & 1) && (h >> 1) < P && (w >> 1) < Q)
       val = ldg8(dy, ((n * P + (h >> 1)) * Q + (w >> 1)) * vpr + v);
     stg8(u, i, val);

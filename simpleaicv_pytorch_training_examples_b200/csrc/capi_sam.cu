@@ -12,13 +12,11 @@
 
 #include "../../include/saicv_b200.h"
 #include "host_util.h"
+#include "vec8.cuh"
 
 namespace saicv {
 namespace {
 
-struct alignas(16) V8 {
-  __nv_bfloat162 h[4];
-};
 
 int grid1d(long long items, int per_block = 256, int cap = 148 * 16) {
   long long b = (items + per_block - 1) / per_block;
@@ -42,8 +40,7 @@ __global__ void window_partition_kernel(const V8* __restrict__ x, V8* __restrict
     const long long b = t / nwy;
     const int h = wy * ws + iy, w = wx * ws + ix;
     V8 val;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) val.h[k] = __floats2bfloat162_rn(0.f, 0.f);
+    val.zero();
     if (h < H && w < W) val = x[((b * H + h) * W + w) * vpr + v];
     win[i] = val;
   }
@@ -104,7 +101,7 @@ relpos_build_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
       const V8 v = *reinterpret_cast<const V8*>(qrow + i);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 f = __bfloat1622float2(v.h[k]);
+        const float2 f = __bfloat1622float2(v.h(k));
         q[i + 2 * k] = f.x;
         q[i + 2 * k + 1] = f.y;
       }
@@ -115,7 +112,7 @@ relpos_build_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
     for (int i = 0; i < HD; i += 8) {
       V8 o;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o.h[k] = __floats2bfloat162_rn(q[i + 2 * k] * scale, q[i + 2 * k + 1] * scale);
+      for (int k = 0; k < 4; ++k) o.set(k, __floats2bfloat162_rn(q[i + 2 * k] * scale, q[i + 2 * k + 1] * scale));
       *reinterpret_cast<V8*>(qo + i) = o;
       *reinterpret_cast<V8*>(ko + i) = *reinterpret_cast<const V8*>(krow + i);
     }
@@ -167,7 +164,7 @@ relpos_bwd_dq_kernel(const __nv_bfloat16* __restrict__ dqe, const float* __restr
       const V8 v = *reinterpret_cast<const V8*>(g + i);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 f = __bfloat1622float2(v.h[k]);
+        const float2 f = __bfloat1622float2(v.h(k));
         acc[i + 2 * k] = f.x * scale;
         acc[i + 2 * k + 1] = f.y * scale;
       }
@@ -189,82 +186,63 @@ relpos_bwd_dq_kernel(const __nv_bfloat16* __restrict__ dqe, const float* __restr
     for (int i = 0; i < HD; i += 8) {
       V8 o;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o.h[k] = __floats2bfloat162_rn(acc[i + 2 * k], acc[i + 2 * k + 1]);
+      for (int k = 0; k < 4; ++k) o.set(k, __floats2bfloat162_rn(acc[i + 2 * k], acc[i + 2 * k + 1]));
       *reinterpret_cast<V8*>(out + i) = o;
     }
   }
 }
 
-// partial[blk][idx][c] = sum over the block's (bw, head, token) rows and the kh with qh - kh + Sh - 1 == idx of
-// dQe[row][HD + kh] * q[row][c]  (table 0: height) and likewise for the width table.  One thread per (idx, c)
-// pair (strided), rows of the block staged in shared memory; fixed summation order.
+// Table gradients as ONE tensor-core GEMM.  d rel_pos_h[idx][c] = sum over rows r and key rows kh with
+// qh(r) - kh + Sh - 1 == idx of dT_h[r][kh] * q[r][c] (likewise for the width table).  Re-indexing the bias gradients per
+// row, ef[r][idx] = dT_h[r][qh(r) - idx + Sh - 1] and ef[r][nh + idx] = dT_w[r][qw(r) - idx + Sw - 1] (zero where the
+// key index falls outside the grid, and in the padding columns up to NIP), turns both sums into
+//     [d rel_pos_h ; d rel_pos_w] = ef^T [NIP x rows] * qc [rows x HD],
+// the weight-gradient form of the GEMM engine (saicv_linear_wgrad).  This kernel writes ef and the compact copy qc of
+// the (unscaled) q rows; rows are ordered (window, head, token).  One thread per 16-byte piece.
 template <int HD>
 __global__ void __launch_bounds__(256)
-relpos_bwd_table_kernel(const __nv_bfloat16* __restrict__ dqe, const __nv_bfloat16* __restrict__ qkv, float* __restrict__ partial,
-                        int Bw, int H, int Sh, int Sw, int DQK, long long rows_per_block) {
-  constexpr int RT = 32;                 // rows staged per step
-  __shared__ float sq[RT][HD];
-  __shared__ float sd[RT][128];          // dT_h | dT_w of the staged rows (Sh + Sw <= 128)
-  __shared__ int sqh[RT], sqw[RT];
+relpos_shift_kernel(const __nv_bfloat16* __restrict__ dqe, const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ef,
+                    __nv_bfloat16* __restrict__ qc, int Bw, int H, int Sh, int Sw, int DQK, int NIP) {
   const int L = Sh * Sw;
-  const long long total = (long long)Bw * H * L;
-  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(total, r0 + rows_per_block);
-  const int nh = (2 * Sh - 1) * HD, nw = (2 * Sw - 1) * HD, nout = nh + nw;
-  constexpr int MAXO = 16;               // outputs per thread and pass (statically indexed accumulators)
-  for (int o0 = 0; o0 < nout; o0 += 256 * MAXO) {
-    float acc[MAXO];
-#pragma unroll
-    for (int k = 0; k < MAXO; ++k) acc[k] = 0.f;
-    for (long long rb = r0; rb < r1; rb += RT) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < RT * HD; i += 256) {
-        const int rr = i / HD, c = i % HD;
-        const long long r = rb + rr;
-        float v = 0.f;
-        if (r < r1) {
-          const int l = (int)(r % L);
-          const long long bh = r / L;
-          const int h = (int)(bh % H);
-          const long long bw = bh / H;
-          v = __bfloat162float(qkv[((bw * L + l) * 3) * (long long)H * HD + (long long)h * HD + c]);
-        }
-        sq[rr][c] = v;
-      }
-      for (int i = threadIdx.x; i < RT * (Sh + Sw); i += 256) {
-        const int rr = i / (Sh + Sw), j = i % (Sh + Sw);
-        const long long r = rb + rr;
-        sd[rr][j] = r < r1 ? __bfloat162float(dqe[r * DQK + HD + j]) : 0.f;
-      }
-      if (threadIdx.x < RT) {
-        const long long r = rb + threadIdx.x;
-        const int l = (int)(r % L);
-        sqh[threadIdx.x] = l / Sw;
-        sqw[threadIdx.x] = l % Sw;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < MAXO; ++k) {
-        const int o = o0 + k * 256 + threadIdx.x;
-        if (o < nout) {
-          const bool is_h = o < nh;
-          const int oo = is_h ? o : o - nh;
-          const int idx = oo / HD, c = oo % HD;
-          const int lim = is_h ? Sh : Sw;
-          float a = acc[k];
-          for (int rr = 0; rr < RT; ++rr) {
-            // kh = qh - idx + Sh - 1 must be a valid key row (staged rows beyond the block end carry dT = 0)
-            const int kk = (is_h ? sqh[rr] : sqw[rr]) - idx + lim - 1;
-            if (kk >= 0 && kk < lim) a = fmaf(sd[rr][is_h ? kk : Sh + kk], sq[rr][c], a);
-          }
-          acc[k] = a;
-        }
-      }
+  const int ef_pieces = NIP >> 3, pieces = ef_pieces + HD / 8;
+  const int nh = 2 * Sh - 1, nw = 2 * Sw - 1;
+  const long long total = (long long)Bw * H * L * pieces;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int pc = (int)(i % pieces);
+    const long long r = i / pieces;
+    const int l = (int)(r % L);
+    if (pc >= ef_pieces) {
+      const long long bh = r / L;
+      const int h = (int)(bh % H);
+      const long long bw = bh / H;
+      const int c0 = (pc - ef_pieces) * 8;
+      *reinterpret_cast<uint4*>(qc + r * HD + c0) =
+          __ldg(reinterpret_cast<const uint4*>(qkv + ((bw * L + l) * 3) * (long long)H * HD + (long long)h * HD + c0));
+      continue;
     }
+    const int qh = l / Sw, qw = l % Sw;
+    const __nv_bfloat16* g = dqe + r * DQK + HD;
+    const unsigned short* gs = reinterpret_cast<const unsigned short*>(g);
+    uint32_t w[4];
 #pragma unroll
-    for (int k = 0; k < MAXO; ++k) {
-      const int o = o0 + k * 256 + threadIdx.x;
-      if (o < nout) partial[(long long)blockIdx.x * nout + o] = acc[k];
+    for (int k = 0; k < 4; ++k) {
+      unsigned short v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int idx = pc * 8 + 2 * k + e;
+        int src = -1;
+        if (idx < nh) {
+          const int kh = qh - idx + Sh - 1;
+          if (kh >= 0 && kh < Sh) src = kh;
+        } else if (idx < nh + nw) {
+          const int kw = qw - (idx - nh) + Sw - 1;
+          if (kw >= 0 && kw < Sw) src = Sh + kw;
+        }
+        v[e] = src >= 0 ? __ldg(gs + src) : (unsigned short)0;
+      }
+      w[k] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
     }
+    *reinterpret_cast<uint4*>(ef + r * NIP + pc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -325,16 +303,10 @@ int saicv_relpos_build(const void* qkv, const float* rel_pos_h, const float* rel
   return check_launch("relpos_build_kernel");
 }
 
-int saicv_relpos_bwd_blocks(long long rows) {
-  long long b = (rows + 1023) / 1024;
-  if (b > 148) b = 148;
-  return (int)(b < 1 ? 1 : b);
-}
-
-int saicv_relpos_bwd(const void* dqe, const void* qkv, const float* rel_pos_h, const float* rel_pos_w, void* dqkv, float* partial,
-                     float* d_rel_pos_h, float* d_rel_pos_w, int bw, int heads, int hd, int sh, int sw, int dqk, float scale,
-                     int accumulate, void* stream) {
+int saicv_relpos_bwd(const void* dqe, const void* qkv, const float* rel_pos_h, const float* rel_pos_w, void* dqkv, void* ef,
+                     void* qc, int nip, int bw, int heads, int hd, int sh, int sw, int dqk, float scale, void* stream) {
   if (sh + sw > 128) return set_error("saicv_relpos_bwd: Sh + Sw must be <= 128");
+  if (nip % 8 || nip < 2 * sh - 1 + 2 * sw - 1) return set_error("saicv_relpos_bwd: nip must be a multiple of 8 covering both tables");
   const size_t smem = (size_t)(2 * sh - 1 + 2 * sw - 1) * hd * 4;
   const long long rows = (long long)bw * heads * sh * sw;
   const int grid = grid1d(rows, 128, 148 * 8);
@@ -348,18 +320,11 @@ int saicv_relpos_bwd(const void* dqe, const void* qkv, const float* rel_pos_h, c
   }
   SAM_HD_DISPATCH(relpos_bwd_dq_kernel, <<<grid, 128, smem, ST>>>(g, rel_pos_h, rel_pos_w, dq, bw, heads, sh, sw, dqk, scale))
   if (int e = check_launch("relpos_bwd_dq_kernel")) return e;
-  const int nblk = saicv_relpos_bwd_blocks(rows);
-  const long long rpb = (rows + nblk - 1) / nblk;
-  SAM_HD_DISPATCH(relpos_bwd_table_kernel, <<<nblk, 256, 0, ST>>>(g, q, partial, bw, heads, sh, sw, dqk, rpb))
-  if (int e = check_launch("relpos_bwd_table_kernel")) return e;
-  // partial rows: [nh floats for the height table | nw floats for the width table]
-  const long long nh = (long long)(2 * sh - 1) * hd, nw = (long long)(2 * sw - 1) * hd;
-  // fold: out[j] (+)= sum_b partial[b][j]; the two tables are contiguous in `partial` rows but separate outputs
-  // -> reduce into a scratch region at the end of `partial`, then copy (tiny)
-  float* scratch = partial + (long long)nblk * (nh + nw);
-  if (int e = saicv_reduce_partials(partial, scratch, nblk, nh + nw, 0, stream)) return e;
-  if (int e = saicv_reduce_partials(scratch, d_rel_pos_h, 1, nh, accumulate, stream)) return e;
-  return saicv_reduce_partials(scratch + nh, d_rel_pos_w, 1, nw, accumulate, stream);
+  __nv_bfloat16* efp = reinterpret_cast<__nv_bfloat16*>(ef);
+  __nv_bfloat16* qcp = reinterpret_cast<__nv_bfloat16*>(qc);
+  const int sgrid = grid1d(rows * (nip / 8 + hd / 8));
+  SAM_HD_DISPATCH(relpos_shift_kernel, <<<sgrid, 256, 0, ST>>>(g, q, efp, qcp, bw, heads, sh, sw, dqk, nip))
+  return check_launch("relpos_shift_kernel");
 }
 
 }  // extern "C"

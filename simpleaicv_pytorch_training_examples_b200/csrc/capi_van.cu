@@ -10,27 +10,11 @@
 
 #include "../../include/saicv_b200.h"
 #include "host_util.h"
+#include "vec8.cuh"
 
 namespace saicv {
 namespace {
 
-struct alignas(16) V8 {
-  __nv_bfloat162 h[4];
-};
-__device__ __forceinline__ void unpack8(const V8& v, float (&f)[8]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(v.h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ V8 pack8(const float (&f)[8]) {
-  V8 v;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v.h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return v;
-}
 // 8 consecutive elements starting at element index `e` of a bf16 or fp32 tensor
 __device__ __forceinline__ void load8(const void* p, long long e, bool f32, float (&f)[8]) {
   if (f32) {
@@ -404,8 +388,7 @@ __global__ void im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
     const long long n = t / ((long long)Q * P);
     const int h = p * stride - pad + tap / K, w = q * stride - pad + tap % K;
     V8 val;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) val.h[k] = __floats2bfloat162_rn(0.f, 0.f);
+    val.zero();
     if (h >= 0 && h < H && w >= 0 && w < W) val = *reinterpret_cast<const V8*>(x + ((n * H + h) * W + w) * C + v * 8);
     *reinterpret_cast<V8*>(cols + i * 8) = val;
   }

@@ -41,6 +41,11 @@ class GraphedTrainStep:
         self.optimizer.zero_grad()
         return loss.detach()
 
+    def replay(self):
+        """Replays the step on the batch already in the static buffers; returns the loss tensor."""
+        self.graph.replay()
+        return self.static_loss
+
     def __call__(self, x, y):
         """Runs one training step on (x, y) (device tensors of the captured shape); returns the loss tensor
         (valid until the next call)."""

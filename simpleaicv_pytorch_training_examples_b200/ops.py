@@ -574,9 +574,75 @@ def relpos_build(qkv, rel_pos_h, rel_pos_w, bw, heads, hd, sh, sw, scale):
 
 
 def relpos_bwd(dqe, qkv, rel_pos_h, rel_pos_w, dqkv, d_rel_pos_h, d_rel_pos_w, bw, heads, hd, sh, sw, scale, accumulate=False):
+    """dq (from the score-operand gradient dqe) into the q slot of dqkv, and the gradients of the two rel-pos tables as
+    ONE weight-gradient GEMM of the tensor-core engine: [d rel_pos_h ; d rel_pos_w] = ef^T qc (include/saicv_b200.h)."""
     dqk = dqe.shape[-1]
     rows = bw * heads * sh * sw
-    nblk = _lib.load().saicv_relpos_bwd_blocks(rows)
-    partial = torch.empty((nblk + 1) * (2 * sh - 1 + 2 * sw - 1) * hd, device=dqe.device, dtype=torch.float32)
-    _lib.call('saicv_relpos_bwd', _p(dqe), _p(qkv), _p(rel_pos_h), _p(rel_pos_w), _p(dqkv), _p(partial), _p(d_rel_pos_h),
-              _p(d_rel_pos_w), bw, heads, hd, sh, sw, dqk, scale, int(accumulate), _stream())
+    nh, nw = 2 * sh - 1, 2 * sw - 1
+    nip = (nh + nw + 63) // 64 * 64
+    ef = torch.empty(rows, nip, device=dqe.device, dtype=torch.bfloat16)
+    qc = torch.empty(rows, hd, device=dqe.device, dtype=torch.bfloat16)
+    _lib.call('saicv_relpos_bwd', _p(dqe), _p(qkv), _p(rel_pos_h), _p(rel_pos_w), _p(dqkv), _p(ef), _p(qc), nip,
+              bw, heads, hd, sh, sw, dqk, scale, _stream())
+    part = linear_wgrad(ef, qc)                      # [splits, nip, hd]
+    tables = torch.empty(nip, hd, device=dqe.device, dtype=torch.float32)
+    reduce_partials(part, tables)
+    reduce_partials(tables[:nh].view(1, nh, hd), d_rel_pos_h, accumulate=accumulate)
+    reduce_partials(tables[nh:nh + nw].view(1, nw, hd), d_rel_pos_w, accumulate=accumulate)
+
+
+# ----------------------------------------------------------------------------- DETR transformer glue
+def postln_fwd(z, gamma, beta, eps, pos=None, want_y=True, want_yb=True, want_ypb=False):
+    """Post-LN of the fp32 stream: returns (y fp32 | None, yb bf16 | None, ypb bf16(y + pos[row % pos_rows]) | None, stats)."""
+    rows, c = z.shape
+    assert z.dtype == torch.float32
+    y = torch.empty_like(z) if want_y else None
+    yb = torch.empty(rows, c, device=z.device, dtype=torch.bfloat16) if want_yb else None
+    ypb = torch.empty(rows, c, device=z.device, dtype=torch.bfloat16) if want_ypb else None
+    stats = torch.empty(2, rows, device=z.device, dtype=torch.float32)
+    _lib.call('saicv_postln_fwd', _p(z), _p(gamma), _p(beta), eps, _p(y), _p(yb), _p(pos), pos.shape[0] if pos is not None else 0,
+              _p(ypb), _p(stats), rows, c, _stream())
+    return y, yb, ypb, stats
+
+
+def postln_bwd(dy, z, gamma, stats, dgamma, dbeta, dres=None, want_dz=True, want_dzb=True, accumulate=False):
+    rows, c = z.shape
+    assert dy.dtype == torch.float32 and z.dtype == torch.float32
+    dz = torch.empty_like(z) if want_dz else None
+    dzb = torch.empty(rows, c, device=z.device, dtype=torch.bfloat16) if want_dzb else None
+    _lib.call('saicv_postln_bwd', _p(dy), _p(z), _p(gamma), _p(stats), _p(dres), _p(dz), _p(dzb), _p(partial_ws(z.device, 2 * c)),
+              _p(dgamma), _p(dbeta), rows, c, int(accumulate), _stream())
+    return dz, dzb
+
+
+def add_pos_cast(x, pos=None, want_xb=True, want_xpb=True):
+    rows, c = x.shape
+    xb = torch.empty(rows, c, device=x.device, dtype=torch.bfloat16) if want_xb else None
+    xpb = torch.empty(rows, c, device=x.device, dtype=torch.bfloat16) if (want_xpb and pos is not None) else None
+    _lib.call('saicv_add_pos_cast', _p(x), _p(pos), pos.shape[0] if pos is not None else 0, _p(xb), _p(xpb), rows, c, _stream())
+    return xb, xpb
+
+
+def dropout(x, p, seed, resid=None, out_f32=None, out=None):
+    """out = keep ? x / (1 - p) : 0 (+ resid); counter-hash mask (csrc/dropout_hash.cuh), same seed => same mask."""
+    if out_f32 is None:
+        out_f32 = x.dtype == torch.float32 or resid is not None
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    _lib.call('saicv_dropout', _p(x), int(x.dtype == torch.float32), _p(resid), _p(out), int(out_f32), x.numel(), float(p), int(seed),
+              _stream())
+    return out
+
+
+def heads_pack(src, col0, b, l, h, hd, dp, scale=1.0, extra=None, extra_const=0.0):
+    """src bf16 [b*l, ld] -> [b, h, l, dp]: head columns scaled, column hd = extra[b*l] (or the constant), rest 0."""
+    dst = torch.empty(b, h, l, dp, device=src.device, dtype=torch.bfloat16)
+    _lib.call('saicv_heads_pack', _p(src), src.shape[1], col0, _p(extra), float(extra_const), _p(dst), b, l, h, hd, dp, float(scale), _stream())
+    return dst
+
+
+def heads_unpack(src, dst, col0, hd, scale=1.0):
+    """src bf16 [b, h, l, dp] -> dst bf16 [b*l, ld] columns col0 .. col0 + h*hd (the leading hd columns of every head, scaled)."""
+    b, h, l, dp = src.shape
+    _lib.call('saicv_heads_unpack', _p(src), _p(dst), dst.shape[1], col0, b, l, h, hd, dp, float(scale), _stream())
+    return dst
