@@ -324,11 +324,12 @@ int saicv_postln_bwd(const float* dy, const float* z, const float* gamma, const 
 /* xb = bf16(x) (nullable), xpb = bf16(x + pos[row % pos_rows]) (nullable); x fp32 [rows][c]. */
 int saicv_add_pos_cast(const float* x, const float* pos, long long pos_rows, void* xb, void* xpb, long long rows,
                        int c, void* stream);
-/* Dropout with the counter hash of csrc/dropout_hash.cuh over the element index: out = keep ? in / (1 - p) : 0
- * (+ resid, fp32, only with an fp32 out).  in / out are bf16 or fp32 (flags); the same call on a gradient with the
- * same seed is the backward pass.  n %% 4 == 0. */
-int saicv_dropout(const void* in, int in_f32, const float* resid, void* out, int out_f32, long long n, float p,
-                  unsigned long long seed, void* stream);
+/* Dropout with the counter hash of csrc/dropout_hash.cuh over the element index:
+ * out = (keep ? in / (1 - p) : 0) * (row_scale ? row_scale[index / elems_per_scale] : 1) (+ resid, fp32, only with an
+ * fp32 out).  row_scale is the per-sample drop-path scale of the branch (vit.py:102-135).  in / out are bf16 or fp32
+ * (flags); the same call on a gradient with the same seed is the backward pass.  n %% 4 == 0. */
+int saicv_dropout(const void* in, int in_f32, const float* resid, const float* row_scale, long long elems_per_scale,
+                  void* out, int out_f32, long long n, float p, unsigned long long seed, void* stream);
 /* Per-head packing of projected rows into a score operand: dst bf16 [b][h][l][dp],
  * dst[.., 0:hd] = src[(b*l + l') * ld + col0 + head*hd + :] * scale, dst[.., hd] = extra ? extra[b*l + l'] :
  * extra_const (the column that carries nn.MultiheadAttention's additive float key_padding_mask against a constant-1

@@ -142,13 +142,16 @@ def _mha(sd, name, q_in, k_in, v_in, key_bias, fns):
     k = rb(F.linear(k_in, rw(w[c:2 * c]), b[c:2 * c]))
     v = rb(F.linear(v_in, rw(w[2 * c:]), b[2 * c:]))
     B, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
-    q = rb(q * hd ** -0.5)                                    # the scaled copy of q is the stored score operand
+    if key_bias is not None:
+        q = rb(q * hd ** -0.5)                                # biased path: the scaled copy of q is a stored score operand
     q = q.view(B, Lq, HEADS, hd).transpose(1, 2)
     k = k.view(B, Lk, HEADS, hd).transpose(1, 2)
     v = v.view(B, Lk, HEADS, hd).transpose(1, 2)
     s = q @ k.transpose(-2, -1)
     if key_bias is not None:
         s = s + key_bias.view(B, 1, 1, Lk)
+    else:
+        s = s * hd ** -0.5                                    # unbiased path: the kernel scales the fp32 scores
     a = s.softmax(dim=-1)
     o = rb((rv(a) @ v).transpose(1, 2).reshape(B, Lq, c))
     return rg(F.linear(o, rw(sd[f'{name}.out_proj.weight']))) + sd[f'{name}.out_proj.bias']

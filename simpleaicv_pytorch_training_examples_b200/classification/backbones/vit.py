@@ -119,10 +119,6 @@ class ViT(nn.Module):
         if not x.is_cuda:
             raise RuntimeError('this model runs on B200 kernels only; move the batch to the GPU '
                                '(no CPU fallback exists)')
-        if self.use_gradient_checkpoint:
-            raise NotImplementedError('use_gradient_checkpoint is not implemented by the B200 runtime yet')
-        if self.training and self.dropout_prob > 0.:
-            raise NotImplementedError('dropout_prob > 0 is not implemented by the B200 runtime (0 in every shipped ViT config)')
         return run_network(self._runtime(), x.float(), self.training)
 
 

@@ -175,8 +175,9 @@ __global__ void add_pos_cast_kernel(const float* __restrict__ x, const float* __
 // out[i] = keep(i) ? in[i] / (1 - p) : 0  (+ resid[i]); keep(i) = hash(seed, i) >= p * 2^32.  The same call with
 // the same seed applied to a gradient is the backward pass.  4 elements per thread.
 template <bool IN_F32, bool OUT_F32>
-__global__ void dropout_kernel(const void* __restrict__ in, const float* __restrict__ resid, void* __restrict__ out,
-                               long long n4, uint32_t thresh, float inv_keep, uint32_t seed_lo, uint32_t seed_hi) {
+__global__ void dropout_kernel(const void* __restrict__ in, const float* __restrict__ resid, const float* __restrict__ row_scale,
+                               long long elems_per_scale, void* __restrict__ out, long long n4, uint32_t thresh, float inv_keep,
+                               uint32_t seed_lo, uint32_t seed_hi) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v;
     if (IN_F32) {
@@ -187,10 +188,11 @@ __global__ void dropout_kernel(const void* __restrict__ in, const float* __restr
       v = make_float4(a.x, a.y, b.x, b.y);
     }
     const uint32_t hi = (uint32_t)(i >> 30), e = (uint32_t)(i << 2);   // element index = hi * 2^32 + e .. e + 3
-    v.x = dropout_hash(seed_lo, seed_hi, e, hi) >= thresh ? v.x * inv_keep : 0.f;
-    v.y = dropout_hash(seed_lo, seed_hi, e + 1, hi) >= thresh ? v.y * inv_keep : 0.f;
-    v.z = dropout_hash(seed_lo, seed_hi, e + 2, hi) >= thresh ? v.z * inv_keep : 0.f;
-    v.w = dropout_hash(seed_lo, seed_hi, e + 3, hi) >= thresh ? v.w * inv_keep : 0.f;
+    const float sc = row_scale ? inv_keep * row_scale[(i * 4) / elems_per_scale] : inv_keep;   // (elems_per_scale % 4 == 0)
+    v.x = dropout_hash(seed_lo, seed_hi, e, hi) >= thresh ? v.x * sc : 0.f;
+    v.y = dropout_hash(seed_lo, seed_hi, e + 1, hi) >= thresh ? v.y * sc : 0.f;
+    v.z = dropout_hash(seed_lo, seed_hi, e + 2, hi) >= thresh ? v.z * sc : 0.f;
+    v.w = dropout_hash(seed_lo, seed_hi, e + 3, hi) >= thresh ? v.w * sc : 0.f;
     if (resid) {
       const float4 r = reinterpret_cast<const float4*>(resid)[i];
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
@@ -319,18 +321,19 @@ int saicv_add_pos_cast(const float* x, const float* pos, long long pos_rows, voi
   return check_launch("add_pos_cast_kernel");
 }
 
-int saicv_dropout(const void* in, int in_f32, const float* resid, void* out, int out_f32, long long n, float p,
-                  unsigned long long seed, void* stream) {
+int saicv_dropout(const void* in, int in_f32, const float* resid, const float* row_scale, long long elems_per_scale, void* out,
+                  int out_f32, long long n, float p, unsigned long long seed, void* stream) {
+  if (row_scale && (elems_per_scale <= 0 || elems_per_scale % 4)) return set_error("saicv_dropout: elems_per_scale must be a positive multiple of 4");
   if (n % 4) return set_error("saicv_dropout: n %% 4 != 0");
   if (!(p >= 0.f && p < 1.f)) return set_error("saicv_dropout: p must be in [0, 1)");
   if (resid && !out_f32) return set_error("saicv_dropout: a residual needs an fp32 output");
   const uint32_t thresh = dropout_threshold(p), lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
   const float inv_keep = 1.f / (1.f - p);
   const int grid = grid_1d(n / 4);
-  if (in_f32 && out_f32) dropout_kernel<true, true><<<grid, 256, 0, ST>>>(in, resid, out, n / 4, thresh, inv_keep, lo, hi);
-  else if (in_f32) dropout_kernel<true, false><<<grid, 256, 0, ST>>>(in, resid, out, n / 4, thresh, inv_keep, lo, hi);
-  else if (out_f32) dropout_kernel<false, true><<<grid, 256, 0, ST>>>(in, resid, out, n / 4, thresh, inv_keep, lo, hi);
-  else dropout_kernel<false, false><<<grid, 256, 0, ST>>>(in, resid, out, n / 4, thresh, inv_keep, lo, hi);
+  if (in_f32 && out_f32) dropout_kernel<true, true><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, lo, hi);
+  else if (in_f32) dropout_kernel<true, false><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, lo, hi);
+  else if (out_f32) dropout_kernel<false, true><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, lo, hi);
+  else dropout_kernel<false, false><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, lo, hi);
   return check_launch("dropout_kernel");
 }
 

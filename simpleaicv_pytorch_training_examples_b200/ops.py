@@ -405,7 +405,7 @@ def pack_key_mask(mask, lk):
     return w.to(torch.int32).contiguous()
 
 
-def _attn_args(q, k, v, out, lse, scale, mask_bits):
+def _attn_args(q, k, v, out, lse, scale, mask_bits, dropout_p=0.0, dropout_seed=0):
     a = _lib.AttnArgs()
     b, h, lq, dqk = q.shape
     lk, dv = k.shape[2], v.shape[3]
@@ -415,29 +415,32 @@ def _attn_args(q, k, v, out, lse, scale, mask_bits):
     a.key_mask_bits = mask_bits.data_ptr() if mask_bits is not None else None
     a.mask_words = mask_bits.shape[1] if mask_bits is not None else 0
     a.b, a.h, a.lq, a.lk, a.dqk, a.dv, a.scale = b, h, lq, lk, dqk, dv, scale
+    a.dropout_p, a.dropout_seed = float(dropout_p), int(dropout_seed)
     return a
 
 
-def attn_fwd(q, k, v, scale, out=None, mask_bits=None):
+def attn_fwd(q, k, v, scale, out=None, mask_bits=None, dropout_p=0.0, dropout_seed=0):
     """General fused attention.  q [B, H, Lq, Dqk], k [B, H, Lk, Dqk], v [B, H, Lk, Dv]: bf16 VIEWS with a
     contiguous last dimension (any batch / head / row strides).  out: [B, H, Lq, Dv] view to write (default:
-    a [B, Lq, H, Dv] buffer viewed as [B, H, Lq, Dv], i.e. heads concatenated per token).  Returns (out, lse)."""
+    a [B, Lq, H, Dv] buffer viewed as [B, H, Lq, Dv], i.e. heads concatenated per token).  dropout_p > 0: dropout on
+    the attention probabilities with the counter-hash mask of dropout_seed (pass the same pair to attn_bwd).
+    Returns (out, lse)."""
     b, h, lq, _ = q.shape
     dv = v.shape[3]
     if out is None:
         out = torch.empty(b, lq, h, dv, device=q.device, dtype=torch.bfloat16).permute(0, 2, 1, 3)
     lse = torch.empty(b, h, lq, device=q.device, dtype=torch.float32)
-    a = _attn_args(q, k, v, out, lse, scale, mask_bits)
+    a = _attn_args(q, k, v, out, lse, scale, mask_bits, dropout_p, dropout_seed)
     _lib.call('saicv_attn_fwd', ctypes.byref(a), _stream())
     return out, lse
 
 
-def attn_bwd(q, k, v, out, lse, dout, scale, dq, dk, dv, dk_cols=0, mask_bits=None):
+def attn_bwd(q, k, v, out, lse, dout, scale, dq, dk, dv, dk_cols=0, mask_bits=None, dropout_p=0.0, dropout_seed=0):
     """Gradients of attn_fwd written into the given [B, H, L, D] views dq (Dqk cols), dk (leading dk_cols
     columns; 0 = all) and dv."""
     assert dout.stride() == out.stride(), 'dout must have the layout of out'
     a = _lib.AttnBwdArgs()
-    a.fwd = _attn_args(q, k, v, out, lse, scale, mask_bits)
+    a.fwd = _attn_args(q, k, v, out, lse, scale, mask_bits, dropout_p, dropout_seed)
     delta = torch.empty_like(lse)
     a.dout, a.delta = dout.data_ptr(), delta.data_ptr()
     a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
@@ -592,12 +595,13 @@ def relpos_bwd(dqe, qkv, rel_pos_h, rel_pos_w, dqkv, d_rel_pos_h, d_rel_pos_w, b
 
 
 # ----------------------------------------------------------------------------- DETR transformer glue
-def postln_fwd(z, gamma, beta, eps, pos=None, want_y=True, want_yb=True, want_ypb=False):
-    """Post-LN of the fp32 stream: returns (y fp32 | None, yb bf16 | None, ypb bf16(y + pos[row % pos_rows]) | None, stats)."""
+def postln_fwd(z, gamma, beta, eps, pos=None, want_y=True, want_yb=True, want_ypb=False, yb_out=None):
+    """Post-LN of the fp32 stream: returns (y fp32 | None, yb bf16 | None, ypb bf16(y + pos[row % pos_rows]) | None, stats).
+    yb_out: bf16 [rows, c] buffer to receive yb."""
     rows, c = z.shape
     assert z.dtype == torch.float32
     y = torch.empty_like(z) if want_y else None
-    yb = torch.empty(rows, c, device=z.device, dtype=torch.bfloat16) if want_yb else None
+    yb = yb_out if yb_out is not None else (torch.empty(rows, c, device=z.device, dtype=torch.bfloat16) if want_yb else None)
     ypb = torch.empty(rows, c, device=z.device, dtype=torch.bfloat16) if want_ypb else None
     stats = torch.empty(2, rows, device=z.device, dtype=torch.float32)
     _lib.call('saicv_postln_fwd', _p(z), _p(gamma), _p(beta), eps, _p(y), _p(yb), _p(pos), pos.shape[0] if pos is not None else 0,
@@ -623,14 +627,15 @@ def add_pos_cast(x, pos=None, want_xb=True, want_xpb=True):
     return xb, xpb
 
 
-def dropout(x, p, seed, resid=None, out_f32=None, out=None):
-    """out = keep ? x / (1 - p) : 0 (+ resid); counter-hash mask (csrc/dropout_hash.cuh), same seed => same mask."""
+def dropout(x, p, seed, resid=None, out_f32=None, out=None, row_scale=None, elems_per_scale=0):
+    """out = (keep ? x / (1 - p) : 0) * row_scale[index // elems_per_scale] (+ resid); counter-hash mask
+    (csrc/dropout_hash.cuh), same seed => same mask."""
     if out_f32 is None:
         out_f32 = x.dtype == torch.float32 or resid is not None
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
-    _lib.call('saicv_dropout', _p(x), int(x.dtype == torch.float32), _p(resid), _p(out), int(out_f32), x.numel(), float(p), int(seed),
-              _stream())
+    _lib.call('saicv_dropout', _p(x), int(x.dtype == torch.float32), _p(resid), _p(row_scale), elems_per_scale, _p(out), int(out_f32),
+              x.numel(), float(p), int(seed), _stream())
     return out
 
 

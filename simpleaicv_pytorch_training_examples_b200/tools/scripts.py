@@ -84,6 +84,72 @@ def train_classification(train_loader, model, criterion, optimizer, scheduler, e
     return losses.avg * accum
 
 
+def train_detection(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config):
+    """One epoch of detection training with the reference's step semantics (tools/scripts.py:900-1092): DETR batches carry
+    'image', 'scaled_annots' and 'mask'; the criterion returns a dict of loss terms whose sum is differentiated; NaN / inf
+    / zero-loss guards skip the batch on every rank; gradient accumulation under no_sync(); clipping; per-iteration LR.
+    The reference all-reduces the skip flag, every loss term and the total with one host sync each (>= 20 per step for
+    DETR's 18 terms); here they travel in ONE coalesced all-reduce and are read with one sync."""
+    losses = AverageMeter()
+    model.train()
+    accum = config.accumulation_steps
+    assert accum >= 1, 'illegal accumulation_steps!'
+    iters = len(train_loader.dataset) // config.batch_size
+    group = getattr(config, 'group', None)
+    world = _world()
+    is_detr = 'detr' in config.network
+    iter_index = 1
+    from .utils import CudaPrefetcher
+    for _, data in enumerate(CudaPrefetcher(train_loader)):
+        images = data['image']
+        targets = data['scaled_annots'] if is_detr else data['annots']
+        bad = (~torch.isfinite(images)).any() | (~torch.isfinite(targets)).any()
+        outs = model(images, data['mask']) if is_detr else model(images)
+        loss_value = criterion(outs, targets)
+        names = list(loss_value)
+        terms = torch.stack([loss_value[k].float() for k in names])
+        loss = terms.sum()
+        bad = bad | (~torch.isfinite(terms)).any() | (loss == 0.)
+        loss = loss / accum
+        sync_step = iter_index % accum == 0
+        if sync_step or not hasattr(model, 'no_sync'):
+            loss.backward()
+        else:
+            with model.no_sync():
+                loss.backward()
+        if getattr(config, 'skip_inf_nan_grad', False):
+            for p in model.parameters():
+                if p.grad is not None:
+                    bad = bad | (~torch.isfinite(p.grad)).any()
+        stat = torch.cat([bad.float().view(1), loss.detach().float().view(1), terms.detach() / accum])
+        if world > 1:
+            dist.all_reduce(stat, op=dist.ReduceOp.SUM, group=group)
+        stat = stat.tolist()  # the one host sync of the step
+        skip_count, loss_sum, term_sums = stat[0], stat[1], stat[2:]
+        if skip_count > 0:
+            logger.info('skip this batch!') if _is_master(config) else None
+            optimizer.zero_grad()
+            continue
+        if sync_step:
+            if getattr(config, 'clip_grad_value', 0) and config.clip_grad_value > 0:
+                torch.nn.utils.clip_grad_value_(model.parameters(), config.clip_grad_value)
+            if getattr(config, 'clip_max_norm', 0) and config.clip_max_norm > 0:
+                torch.nn.utils.clip_grad_norm_(model.parameters(), config.clip_max_norm)
+            optimizer.step()
+            optimizer.zero_grad()
+            if getattr(config, 'use_ema_model', False):
+                config.ema_model.update(model)
+            losses.update(loss_sum / world, images.size(0))
+            scheduler.step(optimizer, iter_index / iters + (epoch - 1))
+        if iter_index % int(config.print_interval * accum) == 0 and _is_master(config):
+            msg = (f'train: epoch {epoch:0>4d}, iter [{iter_index // accum:0>5d}, {iters // accum:0>5d}], lr: {scheduler.current_lr:.6f}, '
+                   f'total_loss: {loss_sum / world * accum:.4f}, ')
+            msg += ''.join(f'{k}: {v / world * accum:.4f}, ' for k, v in zip(names, term_sums))
+            logger.info(msg)
+        iter_index += 1
+    return losses.avg * accum
+
+
 @torch.no_grad()
 def test_classification(test_loader, model, criterion, config):
     """Returns (acc1 %, acc5 %, loss); top-k indices come from torch.topk like the reference

@@ -34,6 +34,9 @@ CASES = [
     ('sam_enc_e128_h2_b3_320px', 'sam', 'ViTImageEncoder',
      {'image_size': 320, 'patch_size': 16, 'embedding_planes': 128, 'block_nums': 3, 'head_nums': 2, 'out_planes': 256,
       'window_size': 14, 'global_attn_indexes': (1,)}, 0, (1, 3, 320, 320), 8, False),
+    # DETR (detection/models/detr.py): 6 + 6 transformer layers, 100 queries, padded right / bottom borders so that the
+    # additive key-padding bias matters; dropout set to 0 on the reference; outputs = (cls, reg), loss = oracle.detr.surrogate_loss
+    ('resnet18_detr_b2_128x160', 'detr', 'resnet18_detr', {}, 80, (2, 3, 128, 160), 3, True),
 ]
 
 
@@ -47,6 +50,26 @@ def sam_randomize(tensors, seed):
 
 def sam_proj(shape, out_planes, grid, seed):
     return torch.randn(shape[0], out_planes, grid, grid, generator=torch.Generator().manual_seed(500 + seed))
+
+
+def detr_masks(shape):
+    """Deterministic padding masks [B, H, W] (True = padding): image b keeps the top-left (H - 32 b') x (W - 40 b'') part."""
+    b, _, h, w = shape
+    m = torch.zeros(b, h, w, dtype=torch.bool)
+    for i in range(b):
+        if i % 2 == 0:
+            m[i, :, w - 40:] = True
+        else:
+            m[i, h - 32:, :] = True
+    return m
+
+
+def detr_disable_dropout(model):
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, torch.nn.MultiheadAttention):
+            mod.dropout = 0.0
 
 
 def oracle_init(family, arch, kwargs, nc, seed):
@@ -69,6 +92,9 @@ def oracle_init(family, arch, kwargs, nc, seed):
         sd = sam_encoder.init_state(seed, k['image_size'], k['patch_size'], k['embedding_planes'], k['block_nums'], k['head_nums'], 4,
                                     k['out_planes'], k['window_size'], k['global_attn_indexes'])
         return sd
+    if family == 'detr':
+        from oracle import detr
+        return detr.init_state(arch, seed, num_classes=nc)
     raise KeyError(family)
 
 
@@ -101,6 +127,13 @@ def oracle_run(family, arch, kwargs, sd, x, y, training=True):
         if training:
             return sam_encoder.loss_and_grads(sd, x, y, k['head_nums'], k['window_size'], k['global_attn_indexes'], k['patch_size'])
         return sam_encoder.forward(sd, x, k['head_nums'], k['window_size'], k['global_attn_indexes'], k['patch_size'])
+    if family == 'detr':
+        from oracle import detr
+        masks = detr_masks(tuple(x.shape))
+        if training:
+            cls, reg, loss, grads = detr.loss_and_grads(sd, x, masks, arch)
+            return (cls, reg), loss, grads
+        return detr.forward(sd, x, masks, arch, training=False)
     raise KeyError(family)
 
 
@@ -128,6 +161,9 @@ def main():
         if family == 'sam':
             enc = ref_import.module('SimpleAICV.interactive_segmentation.models.segment_anything.image_encoder')
             model = enc.ViTImageEncoder(**kwargs)
+        elif family == 'detr':
+            model = ref_import.module('SimpleAICV.detection.models').__dict__[arch](num_classes=nc, **kwargs)
+            detr_disable_dropout(model)
         else:
             model = backbones.__dict__[arch](num_classes=nc, **kwargs)
         sd0 = {k: v.clone() for k, v in model.state_dict().items()}
@@ -141,6 +177,10 @@ def main():
             y = sam_proj(shape, kwargs['out_planes'], kwargs['image_size'] // kwargs['patch_size'], seed)
             logits = model(x)
             loss = (logits.float() * y).mean()
+        elif family == 'detr':
+            from oracle import detr as odetr
+            logits, reg = model(x, detr_masks(shape))
+            loss = odetr.surrogate_loss(logits, reg)
         else:
             logits = model(x)
             loss = CELoss()(logits, y)
@@ -149,8 +189,8 @@ def main():
             'family': family, 'arch': arch, 'kwargs': kwargs, 'num_classes': nc, 'seed': seed, 'shape': shape, 'y': y,
             'x_digest': (float(x.double().sum()), x.flatten()[:4].clone()),
             'logits': logits.detach(), 'loss': loss.detach(),
-            'grad_norm': {n: p.grad.norm().item() for n, p in model.named_parameters()},
-            'grad_head': {n: p.grad.flatten()[:4].clone() for n, p in model.named_parameters()},
+            'grad_norm': {n: p.grad.norm().item() for n, p in model.named_parameters() if p.grad is not None},
+            'grad_head': {n: p.grad.flatten()[:4].clone() for n, p in model.named_parameters() if p.grad is not None},
             'buffers': dict([(k, v.clone()) for k, v in model.state_dict().items() if k.endswith('running_mean')][:2]),
             'torch_version': torch.__version__,
             'reference_commit': '14b1826',
@@ -159,7 +199,11 @@ def main():
             fix['x'] = x
         model.eval()
         with torch.no_grad():
-            fix['eval_logits'] = model(x).clone()
+            if family == 'detr':
+                fix['reg'] = reg.detach()
+                fix['eval_logits'], fix['eval_reg'] = [t.clone() for t in model(x, detr_masks(shape))]
+            else:
+                fix['eval_logits'] = model(x).clone()
         torch.save(fix, os.path.join(HERE, tag + '.pt'))
         print(tag, 'loss', float(loss), os.path.getsize(os.path.join(HERE, tag + '.pt')), 'bytes')
 

@@ -176,3 +176,47 @@ def test_sam_encoder_oracle_and_constructor_match_reference():
     for n, p in r.named_parameters():
         rel = ((gr[n] - p.grad).norm() / p.grad.norm().clamp_min(1e-20)).item()
         assert rel < 1e-4, (n, rel)
+
+
+def test_detr_oracle_and_constructor_match_reference():
+    """oracle/detr.py and the B200 DETR shell vs detection/models/detr.py:273-364 (ResNet-18 body, 6 + 6 layers, padded
+    images so that the float key_padding_mask bias matters; dropout zeroed on the reference)."""
+    from oracle import detr as od
+    from simpleaicv_pytorch_training_examples_b200.detection import models as mine
+    ref_models = ref_import.module('SimpleAICV.detection.models')
+    torch.manual_seed(11)
+    r = ref_models.__dict__['resnet18_detr']()
+    torch.manual_seed(11)
+    m = mine.resnet18_detr()
+    sd = od.init_state('resnet18_detr', 11)
+    rs, ms = r.state_dict(), m.state_dict()
+    assert list(rs.keys()) == list(ms.keys()) == list(sd.keys())
+    assert all(torch.equal(rs[k], ms[k]) and torch.equal(rs[k], sd[k]) for k in rs)
+    for mod in r.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, torch.nn.MultiheadAttention):
+            mod.dropout = 0.0
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 3, 96, 128, generator=g)
+    masks = torch.zeros(2, 96, 128, dtype=torch.bool)
+    masks[0, :, 96:] = True
+    masks[1, 64:, :] = True
+    r.train()
+    cls_r, reg_r = r(x, masks)
+    od.surrogate_loss(cls_r, reg_r).backward()
+    cls_o, reg_o, _, gr = od.loss_and_grads(sd, x, masks, 'resnet18_detr')
+    torch.testing.assert_close(cls_o, cls_r.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(reg_o, reg_r.detach(), rtol=1e-4, atol=1e-4)
+    for n, p in r.named_parameters():
+        if p.grad is None:
+            assert float(gr[n].abs().max()) == 0.0, n
+            continue
+        rel = ((gr[n] - p.grad).norm() / p.grad.norm().clamp_min(1e-20)).item()
+        assert rel < 5e-4, (n, rel)      # fp32 summation order in the BN / long-reduction gradients
+    # the masked-out keys are NOT excluded by the reference: a bool mask would give a different result
+    r.eval()
+    with torch.no_grad():
+        a = r(x, masks)[0]
+        b = r(x, torch.zeros_like(masks))[0]
+    assert (a - b).abs().max() > 1e-4

@@ -122,3 +122,56 @@ def test_vit_drop_path_runs_and_scales():
     out = m(x)
     out.float().sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+def _small_vit(**kw):
+    from simpleaicv_pytorch_training_examples_b200.classification import backbones
+    torch.manual_seed(0)
+    m = backbones.vit_base_patch16(image_size=64, num_classes=10, **kw).cuda().train()
+    with torch.no_grad():
+        m.fc.weight.mul_(1000.)
+    return m
+
+
+def _step(model, x, y, seed):
+    for p in model.parameters():
+        p.grad = None
+    torch.manual_seed(seed)
+    out = model(x)
+    torch.nn.functional.cross_entropy(out.float(), y).backward()
+    torch.cuda.synchronize()
+    return out.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters()}
+
+
+def test_vit_gradient_checkpoint_is_bit_identical():
+    """use_gradient_checkpoint (vit.py:247-249): the backward re-runs each block from its saved input with the
+    forward's drop-path draws and dropout seeds; the kernels are deterministic, so every gradient matches bit for bit."""
+    g = torch.Generator().manual_seed(5)
+    x, y = torch.randn(4, 3, 64, 64, generator=g).cuda(), torch.randint(0, 10, (4,), generator=g).cuda()
+    for kw in (dict(drop_path_prob=0.2), dict(drop_path_prob=0.1, dropout_prob=0.1)):
+        a = _step(_small_vit(**kw), x, y, 3)
+        b = _step(_small_vit(use_gradient_checkpoint=True, **kw), x, y, 3)
+        assert torch.equal(a[0], b[0])
+        for n in a[1]:
+            assert torch.equal(a[1][n], b[1][n]), n
+
+
+def test_vit_dropout_paths():
+    """dropout_prob > 0 (attention probabilities, after proj, after GELU, after fc2, embedding): reproducible under the
+    same seed, different across seeds, and with p -> 0 (every element kept, scale 1) identical to the p = 0 kernels'
+    result up to bf16 rounding of the separately stored branch output."""
+    g = torch.Generator().manual_seed(6)
+    x, y = torch.randn(4, 3, 64, 64, generator=g).cuda(), torch.randint(0, 10, (4,), generator=g).cuda()
+    m = _small_vit(dropout_prob=0.1)
+    a, b, c = _step(m, x, y, 1), _step(m, x, y, 1), _step(m, x, y, 2)
+    assert torch.equal(a[0], b[0]) and all(torch.equal(a[1][n], b[1][n]) for n in a[1])
+    assert not torch.equal(a[0], c[0])
+    assert all(torch.isfinite(v).all() for v in c[1].values())
+    base = _step(_small_vit(), x, y, 1)
+    tiny = _step(_small_vit(dropout_prob=1e-9), x, y, 1)
+    assert _rel_l2(tiny[0], base[0]) < 2e-2
+    bad = [(n, _rel_l2(tiny[1][n], base[1][n])) for n in base[1] if base[1][n].norm() > 0 and _rel_l2(tiny[1][n], base[1][n]) > 5e-2]
+    assert not bad, bad[:8]
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x), m(x))
