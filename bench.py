@@ -406,7 +406,7 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
 
         class _Cfg:
             optimizer = ('AdamW', {'lr': 1e-4, 'global_weight_decay': False, 'weight_decay': 0.05,
-                                   'no_weight_decay_layer_name_list': [], 'capturable': world == 1 or args.graph_ddp})
+                                   'no_weight_decay_layer_name_list': [], 'capturable': world == 1 or not args.no_graph_ddp})
         opt, _ = tutils.build_optimizer(_Cfg, model)
     elif model_name == 'resnet50':
         model = backbones.resnet50(num_classes=1000).to(dev).train()
@@ -415,7 +415,7 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
     else:
         model = backbones.vit_base_patch16(image_size=224, num_classes=1000, drop_path_prob=0.1, global_pool=True).to(dev).train()
         crit = losses.OneHotLabelCELoss().to(dev)
-        opt, _ = tutils.build_optimizer(vit_optimizer_cfg(model, capturable=(world == 1 or args.graph_ddp)), model)
+        opt, _ = tutils.build_optimizer(vit_optimizer_cfg(model, capturable=(world == 1 or not args.no_graph_ddp)), model)
     net = B200DataParallel(model) if world > 1 else model
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
@@ -473,8 +473,8 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
     # side stream while step i computes) and the loss is read back to the host every step
     # At N = 1 the step is replayed from ONE CUDA graph (graph.GraphedTrainStep, part of the package's API): the host
     # reads every step's loss, so without the graph the ~600 C-ABI launches of the next step could not be issued ahead.
-    graphed, graph_note = None, 'eager (N > 1: NCCL work is issued from autograd hooks)'
-    if (world == 1 or args.graph_ddp) and not args.no_graph:
+    graphed, graph_note = None, 'eager launches'
+    if (world == 1 or not args.no_graph_ddp) and not args.no_graph:
         try:
             torch.cuda.empty_cache()
             from simpleaicv_pytorch_training_examples_b200.graph import GraphedTrainStep
@@ -502,6 +502,15 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
 
     e2e_loop(2)
     e2e_ms = timed(lambda: e2e_loop(steps), 1) / steps
+    graph_ddp_check = None
+    if world > 1 and graphed is not None:
+        # every rank trained on its own batches: parameters stay identical across ranks only if the captured all-reduces ran
+        chk = torch.stack([p.detach().double().abs().sum() for p in model.parameters()]).sum().view(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        graph_ddp_check = ('ok: parameters bit-identical on every rank after the captured steps' if float(lo) == float(hi)
+                           else f'FAILED: parameter checksums differ across ranks ({float(lo)} .. {float(hi)})')
     clocks = sampler.stop() if rank == 0 else None
     rec = None
     if rank == 0:
@@ -525,7 +534,7 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
                        'h2d_bytes_per_step': (x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()) * world,
                        'd2h_bytes_per_step': 4 * world, 'mode': graph_note},
                'gpu_launches': int(launches), 'roofline': roof, 'clocks': clocks, 'workload': WORKLOADS[model_name],
-               'ddp_check': ddp_check, 'eager_ms_per_step': eager_ms_step, 'per_gpu_batch': B, 'timed_steps': steps,
+               'ddp_check': ddp_check, 'graph_ddp_check': graph_ddp_check, 'eager_ms_per_step': eager_ms_step, 'per_gpu_batch': B, 'timed_steps': steps,
                'value_mode': graph_note}
     del model, net, opt
     torch.cuda.empty_cache()
@@ -563,6 +572,8 @@ def run_b200(args, rank, world, local_rank):
     }
     if main.get('ddp_check'):
         line['ddp_check'] = main['ddp_check']
+    if main.get('graph_ddp_check'):
+        line['graph_ddp_check'] = main['graph_ddp_check']
     SUB = ('metric', 'value', 'unit', 'ms_per_step', 'eager_ms_per_step', 'value_mode', 'e2e', 'gpu_launches', 'roofline', 'clocks',
            'workload', 'per_gpu_batch', 'timed_steps')
     line['eager_ms_per_step'], line['value_mode'] = main['eager_ms_per_step'], main['value_mode']
@@ -593,7 +604,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-second-model', action='store_true', help='skip the sub-record of the other BASELINE model')
     ap.add_argument('--sam', action='store_true', help='add the SAM ViT-H image-encoder sub-record (BASELINE configs[3]: bs8, 1024x1024)')
-    ap.add_argument('--graph-ddp', action='store_true', help='N > 1: capture the step (NCCL all-reduces included) in one CUDA graph too')
+    ap.add_argument('--no-graph-ddp', action='store_true',
+                    help='N > 1: launch the step eagerly instead of capturing it (NCCL bucket all-reduces included) in one CUDA graph')
     ap.add_argument('--no-graph', action='store_true', help='end-to-end loop without the CUDA graph (eager launches)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))

@@ -244,20 +244,26 @@ int saicv_window_partition(const void* x, void* windows, int b, int h, int w, in
 int saicv_window_unpartition(const void* windows, void* x, int b, int h, int w, int c, int ws, void* stream);
 /* x[b][...] += pos[...] (fp32, in place): tokens + pos_embed (:315); per_batch = elements of pos. */
 int saicv_add_pos_embed(float* x, const float* pos, int b, long long per_batch, void* stream);
-/* Decomposed relative-position bias (:82-144) as extra score columns for saicv_attn_fwd (scale 1):
- *   qe[bw][head][l] = [q*scale | rel_h[l][0..sh) | rel_w[l][0..sw) | 0..],  ke = [k | onehot(kh) | onehot(kw) | 0..]
- * from packed qkv bf16 [bw][sh*sw][3][heads][hd] and the fp32 tables rel_pos_h [2sh-1][hd], rel_pos_w
- * [2sw-1][hd]; rows of qe / ke have dqk >= hd + sh + sw (multiple of 16) elements. */
-int saicv_relpos_build(const void* qkv, const float* rel_pos_h, const float* rel_pos_w, void* qe, void* ke,
-                       int bw, int heads, int hd, int sh, int sw, int dqk, float scale, void* stream);
-/* Backward: dqe (gradient of qe from saicv_attn_bwd) -> dq into the q slot of dqkv (layout of qkv), plus the two
- * operands of the table-gradient GEMM: ef bf16 [rows][nip] (the bias-column gradients re-indexed per row so that
- * column idx is the rel_pos row it belongs to: height table in columns [0, 2sh-1), width table in
- * [2sh-1, 2sh-1 + 2sw-1), zero padding up to nip, a multiple of 8) and qc bf16 [rows][hd] (the q rows, compact),
- * rows = bw*heads*sh*sw.  [d_rel_pos_h ; d_rel_pos_w] = ef^T qc = saicv_linear_wgrad(ef, qc, M=rows, N=nip, K=hd). */
-int saicv_relpos_bwd(const void* dqe, const void* qkv, const float* rel_pos_h, const float* rel_pos_w,
-                     void* dqkv, void* ef, void* qc, int nip, int bw, int heads, int hd, int sh, int sw, int dqk,
-                     float scale, void* stream);
+/* Decomposed relative-position bias as extra score columns (image_encoder.py:82-144): the bias terms are dot products
+ * of q rows with rel-pos table rows, so they run as GEMMs of the tensor-core engine; these entries move / re-index data
+ * around them.  qkv: bf16 [bw][l = sh*sw][3][heads][hd]; per-head operand rows r are ordered (window, head, token);
+ * nip: a multiple of 8 >= (2sh-1) + (2sw-1); dqk: a multiple of 8 >= hd + sh + sw.
+ *   pack_q:   qc bf16 [rows][hd] = the q rows (unscaled)
+ *   table:    rtab bf16 [nip][hd] = [rel_pos_h ; rel_pos_w ; 0]
+ *   (T bf16 [rows][nip] = saicv_linear_fwd(qc, rtab))
+ *   gather:   qe = [q*scale | T[r][qh-kh+sh-1] | T[r][(2sh-1)+qw-kw+sw-1] | 0], ke = [k | onehot(kh) | onehot(kw) | 0]
+ *   shift:    ef bf16 [rows][nip] = the bias-column gradients of dqe re-indexed so that column idx is its table row
+ *   (dqx fp32 [rows][hd] = saicv_linear_dgrad(ef, rtab); [d rel_pos_h ; d rel_pos_w] = saicv_linear_wgrad(ef, qc))
+ *   dq_combine: q slot of dqkv = bf16(scale * dqe[r][0:hd] + dqx[r]) */
+int saicv_relpos_pack_q(const void* qkv, void* qc, int bw, int heads, int hd, int l, void* stream);
+int saicv_relpos_table(const float* rel_pos_h, const float* rel_pos_w, void* rtab, int sh, int sw, int nip, int hd,
+                       void* stream);
+int saicv_relpos_gather(const void* qkv, const void* t, void* qe, void* ke, int bw, int heads, int hd, int sh, int sw,
+                        int dqk, int nip, float scale, void* stream);
+int saicv_relpos_shift(const void* dqe, void* ef, int bw, int heads, int hd, int sh, int sw, int dqk, int nip,
+                       void* stream);
+int saicv_relpos_dq_combine(const void* dqe, const float* dqx, void* dqkv, int bw, int heads, int hd, int l, int dqk,
+                            float scale, void* stream);
 
 /* ---- fused multi-head attention on tcgen05 / TMEM (csrc/attn_sm100.cuh) ------------------------------
  * Replaces the materialised attention of the reference: vit.py:62-80 (q k^T * scale, softmax, @ v),

@@ -71,158 +71,143 @@ __global__ void add_pos_kernel(float4* __restrict__ x, const float4* __restrict_
   }
 }
 
-// ---- rel-pos score columns.  qkv: [Bw][L][3][H][HD] bf16 (L = Sh*Sw tokens, row-major (qh, qw)).
-// One thread per (bw, head, token).  rel_pos tables live in shared memory as fp32 rounded to bf16 (the
-// reference's einsum consumes them in bf16 under autocast).
-template <int HD>
-__global__ void __launch_bounds__(128)
-relpos_build_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rph, const float* __restrict__ rpw,
-                    __nv_bfloat16* __restrict__ qe, __nv_bfloat16* __restrict__ ke, int Bw, int H, int Sh, int Sw, int DQK,
-                    float scale) {
-  extern __shared__ float stab[];   // [2Sh-1][HD] then [2Sw-1][HD]
-  float* th = stab;
-  float* tw = stab + (2 * Sh - 1) * HD;
-  for (int i = threadIdx.x; i < (2 * Sh - 1) * HD; i += blockDim.x) th[i] = __bfloat162float(__float2bfloat16_rn(rph[i]));
-  for (int i = threadIdx.x; i < (2 * Sw - 1) * HD; i += blockDim.x) tw[i] = __bfloat162float(__float2bfloat16_rn(rpw[i]));
-  __syncthreads();
-  const int L = Sh * Sw;
-  const long long total = (long long)Bw * H * L;
-  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
+// ---- rel-pos score columns.  qkv: [Bw][L][3][H][hd] bf16 (L = Sh*Sw tokens, row-major (qh, qw)); rows r of the
+// per-head operands are ordered (window, head, token).  The bias terms are dot products of q rows with rel-pos table
+// rows, i.e. GEMMs; the kernels here only move / re-index data around three launches of the tensor-core engine:
+//   forward   T[r][idx] = q[r] . Rtab[idx]                      (saicv_linear_fwd:  qc [rows, hd] x rtab [nip, hd]^T)
+//             Qe[r] = [q[r] * scale | T[r][qh - kh + Sh - 1], kh < Sh | T[r][nh + qw - kw + Sw - 1], kw < Sw | 0]
+//   backward  ef[r][idx] = the bias-column gradients re-indexed so that column idx is the table row it belongs to
+//             dq[r]  = scale * dQe[r][0:hd] + ef[r] . Rtab        (saicv_linear_dgrad: ef [rows, nip] x rtab [nip, hd])
+//             dRtab  = ef^T . qc                                  (saicv_linear_wgrad)
+// Rtab = [rel_pos_h ; rel_pos_w ; 0] as bf16 [nip][hd] (the reference's einsum consumes the tables in bf16 under autocast).
+
+// qc[r][0:hd] = q row of (window, head, token) r, unscaled; one thread per 16-byte piece
+__global__ void relpos_packq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ qc, int Bw, int H, int L, int hd) {
+  const int pieces = hd >> 3;
+  const long long total = (long long)Bw * H * L * pieces;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int pc = (int)(i % pieces);
+    const long long r = i / pieces;
     const int l = (int)(r % L);
     const long long bh = r / L;
     const int h = (int)(bh % H);
     const long long bw = bh / H;
-    const int qh = l / Sw, qw = l % Sw;
-    const __nv_bfloat16* qrow = qkv + ((bw * L + l) * 3) * (long long)H * HD + (long long)h * HD;
-    const __nv_bfloat16* krow = qrow + (long long)H * HD;
-    float q[HD];
-#pragma unroll
-    for (int i = 0; i < HD; i += 8) {
-      const V8 v = *reinterpret_cast<const V8*>(qrow + i);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __bfloat1622float2(v.h(k));
-        q[i + 2 * k] = f.x;
-        q[i + 2 * k + 1] = f.y;
-      }
-    }
-    __nv_bfloat16* qo = qe + r * DQK;
-    __nv_bfloat16* ko = ke + r * DQK;
-#pragma unroll
-    for (int i = 0; i < HD; i += 8) {
-      V8 o;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o.set(k, __floats2bfloat162_rn(q[i + 2 * k] * scale, q[i + 2 * k + 1] * scale));
-      *reinterpret_cast<V8*>(qo + i) = o;
-      *reinterpret_cast<V8*>(ko + i) = *reinterpret_cast<const V8*>(krow + i);
-    }
-    for (int j = 0; j < Sh + Sw; ++j) {
-      const float* t = j < Sh ? th + (qh - j + Sh - 1) * HD : tw + (qw - (j - Sh) + Sw - 1) * HD;
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < HD; i += 4) {
-        const float4 tv = *reinterpret_cast<const float4*>(t + i);
-        acc = fmaf(q[i], tv.x, acc);
-        acc = fmaf(q[i + 1], tv.y, acc);
-        acc = fmaf(q[i + 2], tv.z, acc);
-        acc = fmaf(q[i + 3], tv.w, acc);
-      }
-      qo[HD + j] = __float2bfloat16_rn(acc);
-      ko[HD + j] = __float2bfloat16_rn((j < Sh ? (j == qh) : (j - Sh == qw)) ? 1.f : 0.f);
-    }
-    for (int j = HD + Sh + Sw; j < DQK; ++j) {
-      qo[j] = __float2bfloat16_rn(0.f);
-      ko[j] = __float2bfloat16_rn(0.f);
-    }
+    reinterpret_cast<uint4*>(qc)[i] =
+        __ldg(reinterpret_cast<const uint4*>(qkv + ((bw * L + l) * 3) * (long long)H * hd + (long long)h * hd + pc * 8));
   }
 }
 
-// dq[l] = scale * dQe[l][0..HD) + sum_kh dQe[l][HD+kh] * Rh[qh-kh+Sh-1] + sum_kw dQe[l][HD+Sh+kw] * Rw[qw-kw+Sw-1]
-// written into the q slot of dqkv [Bw][L][3][H][HD].
-template <int HD>
-__global__ void __launch_bounds__(128)
-relpos_bwd_dq_kernel(const __nv_bfloat16* __restrict__ dqe, const float* __restrict__ rph, const float* __restrict__ rpw,
-                     __nv_bfloat16* __restrict__ dqkv, int Bw, int H, int Sh, int Sw, int DQK, float scale) {
-  extern __shared__ float stab[];
-  float* th = stab;
-  float* tw = stab + (2 * Sh - 1) * HD;
-  for (int i = threadIdx.x; i < (2 * Sh - 1) * HD; i += blockDim.x) th[i] = __bfloat162float(__float2bfloat16_rn(rph[i]));
-  for (int i = threadIdx.x; i < (2 * Sw - 1) * HD; i += blockDim.x) tw[i] = __bfloat162float(__float2bfloat16_rn(rpw[i]));
-  __syncthreads();
-  const int L = Sh * Sw;
-  const long long total = (long long)Bw * H * L;
-  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
-    const int l = (int)(r % L);
-    const long long bh = r / L;
-    const int h = (int)(bh % H);
-    const long long bw = bh / H;
-    const int qh = l / Sw, qw = l % Sw;
-    const __nv_bfloat16* g = dqe + r * DQK;
-    float acc[HD];
-#pragma unroll
-    for (int i = 0; i < HD; i += 8) {
-      const V8 v = *reinterpret_cast<const V8*>(g + i);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __bfloat1622float2(v.h(k));
-        acc[i + 2 * k] = f.x * scale;
-        acc[i + 2 * k + 1] = f.y * scale;
-      }
-    }
-    for (int j = 0; j < Sh + Sw; ++j) {
-      const float* t = j < Sh ? th + (qh - j + Sh - 1) * HD : tw + (qw - (j - Sh) + Sw - 1) * HD;
-      const float d = __bfloat162float(g[HD + j]);
-#pragma unroll
-      for (int i = 0; i < HD; i += 4) {
-        const float4 tv = *reinterpret_cast<const float4*>(t + i);
-        acc[i] = fmaf(d, tv.x, acc[i]);
-        acc[i + 1] = fmaf(d, tv.y, acc[i + 1]);
-        acc[i + 2] = fmaf(d, tv.z, acc[i + 2]);
-        acc[i + 3] = fmaf(d, tv.w, acc[i + 3]);
-      }
-    }
-    __nv_bfloat16* out = dqkv + ((bw * L + l) * 3) * (long long)H * HD + (long long)h * HD;
-#pragma unroll
-    for (int i = 0; i < HD; i += 8) {
-      V8 o;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o.set(k, __floats2bfloat162_rn(acc[i + 2 * k], acc[i + 2 * k + 1]));
-      *reinterpret_cast<V8*>(out + i) = o;
-    }
+// rtab[idx][c] = bf16(rel_pos_h[idx][c]) for idx < nh, bf16(rel_pos_w[idx - nh][c]) for idx < nh + nw, else 0
+__global__ void relpos_table_kernel(const float* __restrict__ rph, const float* __restrict__ rpw, __nv_bfloat16* __restrict__ rtab,
+                                    int nh, int nw, int nip, int hd) {
+  const int total = nip * hd;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int idx = i / hd, c = i % hd;
+    const float v = idx < nh ? rph[idx * hd + c] : (idx < nh + nw ? rpw[(idx - nh) * hd + c] : 0.f);
+    rtab[i] = __float2bfloat16_rn(v);
   }
 }
 
-// Table gradients as ONE tensor-core GEMM.  d rel_pos_h[idx][c] = sum over rows r and key rows kh with
-// qh(r) - kh + Sh - 1 == idx of dT_h[r][kh] * q[r][c] (likewise for the width table).  Re-indexing the bias gradients per
-// row, ef[r][idx] = dT_h[r][qh(r) - idx + Sh - 1] and ef[r][nh + idx] = dT_w[r][qw(r) - idx + Sw - 1] (zero where the
-// key index falls outside the grid, and in the padding columns up to NIP), turns both sums into
-//     [d rel_pos_h ; d rel_pos_w] = ef^T [NIP x rows] * qc [rows x HD],
-// the weight-gradient form of the GEMM engine (saicv_linear_wgrad).  This kernel writes ef and the compact copy qc of
-// the (unscaled) q rows; rows are ordered (window, head, token).  One thread per 16-byte piece.
-template <int HD>
+// Qe / Ke rows from qkv and T; one thread per 16-byte piece of a Qe row and the matching piece of the Ke row
 __global__ void __launch_bounds__(256)
-relpos_shift_kernel(const __nv_bfloat16* __restrict__ dqe, const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ef,
-                    __nv_bfloat16* __restrict__ qc, int Bw, int H, int Sh, int Sw, int DQK, int NIP) {
+relpos_gather_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ T, __nv_bfloat16* __restrict__ qe,
+                     __nv_bfloat16* __restrict__ ke, int Bw, int H, int Sh, int Sw, int hd, int DQK, int NIP, float scale) {
+  const int L = Sh * Sw, pieces = DQK >> 3, nh = 2 * Sh - 1;
+  const long long total = (long long)Bw * H * L * pieces;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int pc = (int)(i % pieces);
+    const long long r = i / pieces;
+    const int l = (int)(r % L);
+    const long long bh = r / L;
+    const int h = (int)(bh % H);
+    const long long bw = bh / H;
+    const int qh = l / Sw, qw = l % Sw;
+    uint4 qo = make_uint4(0u, 0u, 0u, 0u), ko = make_uint4(0u, 0u, 0u, 0u);
+    if (pc * 8 < hd) {
+      const __nv_bfloat16* qrow = qkv + ((bw * L + l) * 3) * (long long)H * hd + (long long)h * hd + pc * 8;
+      const uint4 qv = __ldg(reinterpret_cast<const uint4*>(qrow));
+      ko = __ldg(reinterpret_cast<const uint4*>(qrow + (long long)H * hd));
+      const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(w[k] << 16) * scale, __uint_as_float(w[k] & 0xffff0000u) * scale);
+        o[k] = *reinterpret_cast<uint32_t*>(&v);
+      }
+      qo = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+      const unsigned short* trow = reinterpret_cast<const unsigned short*>(T + r * NIP);
+      uint32_t qw4[4], kw4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned short qv[2], kv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = pc * 8 + 2 * k + e - hd;           // bias column: key row j (< Sh) or key column j - Sh
+          qv[e] = 0;
+          kv[e] = 0;
+          if (j < Sh) {
+            qv[e] = __ldg(trow + (qh - j + Sh - 1));
+            kv[e] = j == qh ? (unsigned short)0x3F80 : (unsigned short)0;     // bf16 1.0
+          } else if (j < Sh + Sw) {
+            qv[e] = __ldg(trow + nh + (qw - (j - Sh) + Sw - 1));
+            kv[e] = (j - Sh) == qw ? (unsigned short)0x3F80 : (unsigned short)0;
+          }
+        }
+        qw4[k] = (uint32_t)qv[0] | ((uint32_t)qv[1] << 16);
+        kw4[k] = (uint32_t)kv[0] | ((uint32_t)kv[1] << 16);
+      }
+      qo = make_uint4(qw4[0], qw4[1], qw4[2], qw4[3]);
+      ko = make_uint4(kw4[0], kw4[1], kw4[2], kw4[3]);
+    }
+    reinterpret_cast<uint4*>(qe)[i] = qo;
+    reinterpret_cast<uint4*>(ke)[i] = ko;
+  }
+}
+
+// dqkv q slot of row r = bf16(scale * dQe[r][0:hd] + dqx[r][0:hd]); dqx fp32 (the table term from the dgrad GEMM)
+__global__ void relpos_dq_combine_kernel(const __nv_bfloat16* __restrict__ dqe, const float* __restrict__ dqx, __nv_bfloat16* __restrict__ dqkv,
+                                         int Bw, int H, int L, int hd, int DQK, float scale) {
+  const int pieces = hd >> 3;
+  const long long total = (long long)Bw * H * L * pieces;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int pc = (int)(i % pieces);
+    const long long r = i / pieces;
+    const int l = (int)(r % L);
+    const long long bh = r / L;
+    const int h = (int)(bh % H);
+    const long long bw = bh / H;
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(dqe + r * DQK + pc * 8));
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(dqx + r * hd + pc * 8));
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(dqx + r * hd + pc * 8 + 4));
+    const uint32_t w[4] = {g.x, g.y, g.z, g.w};
+    const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat162 v = __floats2bfloat162_rn(fmaf(__uint_as_float(w[k] << 16), scale, xs[2 * k]),
+                                               fmaf(__uint_as_float(w[k] & 0xffff0000u), scale, xs[2 * k + 1]));
+      o[k] = *reinterpret_cast<uint32_t*>(&v);
+    }
+    *reinterpret_cast<uint4*>(dqkv + ((bw * L + l) * 3) * (long long)H * hd + (long long)h * hd + pc * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ef[r][idx] = dT_h[r][qh(r) - idx + Sh - 1] (idx < nh), ef[r][nh + idx] = dT_w[r][qw(r) - idx + Sw - 1] (idx < nw), zero where
+// the key index falls outside the grid and in the padding columns up to NIP; dT = the bias columns of dQe.
+__global__ void __launch_bounds__(256)
+relpos_shift_kernel(const __nv_bfloat16* __restrict__ dqe, __nv_bfloat16* __restrict__ ef, int Bw, int H, int Sh, int Sw, int hd,
+                    int DQK, int NIP) {
   const int L = Sh * Sw;
-  const int ef_pieces = NIP >> 3, pieces = ef_pieces + HD / 8;
+  const int pieces = NIP >> 3;
   const int nh = 2 * Sh - 1, nw = 2 * Sw - 1;
   const long long total = (long long)Bw * H * L * pieces;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int pc = (int)(i % pieces);
     const long long r = i / pieces;
     const int l = (int)(r % L);
-    if (pc >= ef_pieces) {
-      const long long bh = r / L;
-      const int h = (int)(bh % H);
-      const long long bw = bh / H;
-      const int c0 = (pc - ef_pieces) * 8;
-      *reinterpret_cast<uint4*>(qc + r * HD + c0) =
-          __ldg(reinterpret_cast<const uint4*>(qkv + ((bw * L + l) * 3) * (long long)H * HD + (long long)h * HD + c0));
-      continue;
-    }
     const int qh = l / Sw, qw = l % Sw;
-    const __nv_bfloat16* g = dqe + r * DQK + HD;
-    const unsigned short* gs = reinterpret_cast<const unsigned short*>(g);
+    const unsigned short* gs = reinterpret_cast<const unsigned short*>(dqe + r * DQK + hd);
     uint32_t w[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -242,7 +227,7 @@ relpos_shift_kernel(const __nv_bfloat16* __restrict__ dqe, const __nv_bfloat16* 
       }
       w[k] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
     }
-    *reinterpret_cast<uint4*>(ef + r * NIP + pc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(ef)[i] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -277,54 +262,48 @@ int saicv_add_pos_embed(float* x, const float* pos, int b, long long per_batch, 
   return check_launch("add_pos_kernel");
 }
 
-#define SAM_HD_DISPATCH(KERNEL, ...)                                                                      \
-  switch (hd) {                                                                                           \
-    case 32: KERNEL<32> __VA_ARGS__; break;                                                               \
-    case 64: KERNEL<64> __VA_ARGS__; break;                                                               \
-    case 80: KERNEL<80> __VA_ARGS__; break;                                                               \
-    default: return set_error("SAM rel-pos kernels: unsupported head dim %d (32, 64, 80)", hd);            \
-  }
-
-int saicv_relpos_build(const void* qkv, const float* rel_pos_h, const float* rel_pos_w, void* qe, void* ke, int bw, int heads,
-                       int hd, int sh, int sw, int dqk, float scale, void* stream) {
-  if (dqk < hd + sh + sw || dqk % 8) return set_error("saicv_relpos_build: dqk %d too small for %d + %d + %d", dqk, hd, sh, sw);
-  const size_t smem = (size_t)(2 * sh - 1 + 2 * sw - 1) * hd * 4;
-  const long long rows = (long long)bw * heads * sh * sw;
-  const int grid = grid1d(rows, 128, 148 * 8);
-  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
-  __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(qe);
-  __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(ke);
-  if (smem > 48 * 1024) {
-    if (hd == 32) cudaFuncSetAttribute(relpos_build_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (hd == 64) cudaFuncSetAttribute(relpos_build_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (hd == 80) cudaFuncSetAttribute(relpos_build_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  }
-  SAM_HD_DISPATCH(relpos_build_kernel, <<<grid, 128, smem, ST>>>(q, rel_pos_h, rel_pos_w, o1, o2, bw, heads, sh, sw, dqk, scale))
-  return check_launch("relpos_build_kernel");
+static int relpos_check(const char* who, int hd, int sh, int sw, int dqk, int nip) {
+  if (hd % 8 || dqk % 8 || dqk < hd + sh + sw) return set_error("%s: dqk %d too small for %d + %d + %d (or not a multiple of 8)", who, dqk, hd, sh, sw);
+  if (nip % 8 || nip < 2 * sh - 1 + 2 * sw - 1) return set_error("%s: nip must be a multiple of 8 covering both tables", who);
+  return 0;
 }
 
-int saicv_relpos_bwd(const void* dqe, const void* qkv, const float* rel_pos_h, const float* rel_pos_w, void* dqkv, void* ef,
-                     void* qc, int nip, int bw, int heads, int hd, int sh, int sw, int dqk, float scale, void* stream) {
-  if (sh + sw > 128) return set_error("saicv_relpos_bwd: Sh + Sw must be <= 128");
-  if (nip % 8 || nip < 2 * sh - 1 + 2 * sw - 1) return set_error("saicv_relpos_bwd: nip must be a multiple of 8 covering both tables");
-  const size_t smem = (size_t)(2 * sh - 1 + 2 * sw - 1) * hd * 4;
-  const long long rows = (long long)bw * heads * sh * sw;
-  const int grid = grid1d(rows, 128, 148 * 8);
-  const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(dqe);
-  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
-  __nv_bfloat16* dq = reinterpret_cast<__nv_bfloat16*>(dqkv);
-  if (smem > 48 * 1024) {
-    if (hd == 32) cudaFuncSetAttribute(relpos_bwd_dq_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (hd == 64) cudaFuncSetAttribute(relpos_bwd_dq_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (hd == 80) cudaFuncSetAttribute(relpos_bwd_dq_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  }
-  SAM_HD_DISPATCH(relpos_bwd_dq_kernel, <<<grid, 128, smem, ST>>>(g, rel_pos_h, rel_pos_w, dq, bw, heads, sh, sw, dqk, scale))
-  if (int e = check_launch("relpos_bwd_dq_kernel")) return e;
-  __nv_bfloat16* efp = reinterpret_cast<__nv_bfloat16*>(ef);
-  __nv_bfloat16* qcp = reinterpret_cast<__nv_bfloat16*>(qc);
-  const int sgrid = grid1d(rows * (nip / 8 + hd / 8));
-  SAM_HD_DISPATCH(relpos_shift_kernel, <<<sgrid, 256, 0, ST>>>(g, q, efp, qcp, bw, heads, sh, sw, dqk, nip))
+int saicv_relpos_pack_q(const void* qkv, void* qc, int bw, int heads, int hd, int l, void* stream) {
+  if (hd % 8) return set_error("saicv_relpos_pack_q: hd %% 8 != 0");
+  relpos_packq_kernel<<<grid1d((long long)bw * heads * l * (hd / 8)), 256, 0, ST>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(qc), bw, heads, l, hd);
+  return check_launch("relpos_packq_kernel");
+}
+
+int saicv_relpos_table(const float* rel_pos_h, const float* rel_pos_w, void* rtab, int sh, int sw, int nip, int hd, void* stream) {
+  if (nip < 2 * sh - 1 + 2 * sw - 1) return set_error("saicv_relpos_table: nip too small");
+  relpos_table_kernel<<<grid1d((long long)nip * hd), 256, 0, ST>>>(rel_pos_h, rel_pos_w, reinterpret_cast<__nv_bfloat16*>(rtab), 2 * sh - 1,
+                                                                 2 * sw - 1, nip, hd);
+  return check_launch("relpos_table_kernel");
+}
+
+int saicv_relpos_gather(const void* qkv, const void* t, void* qe, void* ke, int bw, int heads, int hd, int sh, int sw, int dqk, int nip,
+                        float scale, void* stream) {
+  if (int e = relpos_check("saicv_relpos_gather", hd, sh, sw, dqk, nip)) return e;
+  relpos_gather_kernel<<<grid1d((long long)bw * heads * sh * sw * (dqk / 8)), 256, 0, ST>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(t), reinterpret_cast<__nv_bfloat16*>(qe),
+      reinterpret_cast<__nv_bfloat16*>(ke), bw, heads, sh, sw, hd, dqk, nip, scale);
+  return check_launch("relpos_gather_kernel");
+}
+
+int saicv_relpos_shift(const void* dqe, void* ef, int bw, int heads, int hd, int sh, int sw, int dqk, int nip, void* stream) {
+  if (int e = relpos_check("saicv_relpos_shift", hd, sh, sw, dqk, nip)) return e;
+  relpos_shift_kernel<<<grid1d((long long)bw * heads * sh * sw * (nip / 8)), 256, 0, ST>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dqe), reinterpret_cast<__nv_bfloat16*>(ef), bw, heads, sh, sw, hd, dqk, nip);
   return check_launch("relpos_shift_kernel");
+}
+
+int saicv_relpos_dq_combine(const void* dqe, const float* dqx, void* dqkv, int bw, int heads, int hd, int l, int dqk, float scale,
+                            void* stream) {
+  if (hd % 8 || dqk % 8) return set_error("saicv_relpos_dq_combine: hd, dqk must be multiples of 8");
+  relpos_dq_combine_kernel<<<grid1d((long long)bw * heads * l * (hd / 8)), 256, 0, ST>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dqe), dqx, reinterpret_cast<__nv_bfloat16*>(dqkv), bw, heads, l, hd, dqk, scale);
+  return check_launch("relpos_dq_combine_kernel");
 }
 
 }  // extern "C"

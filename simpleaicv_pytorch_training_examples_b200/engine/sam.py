@@ -7,7 +7,7 @@ reference under autocast).  Per Block (image_encoder.py:201-239):
     [window partition with zero padding]           csrc/capi_sam.cu            (:32-55)
     qkv = Linear(y)                                tcgen05 GEMM
     att = softmax(q k^T scale + rel_h + rel_w) v   tcgen05 attention; the decomposed rel-pos bias (:82-144) rides in
-                                                   extra score columns built by saicv_relpos_build
+                                                   extra score columns built by ops.relpos_build (one GEMM + gather)
     [window unpartition]                                                       (:58-79)
     x   = x + proj(att);  x = x + lin2(gelu(lin1(LN2(x))))                     GEMM epilogues fuse bias/residual/dGELU
 Neck (:299-311): 1x1 conv -> LayerNorm2d -> 3x3 conv -> LayerNorm2d (LayerNorm over channels = the row LayerNorm
@@ -60,7 +60,8 @@ class _Block:
         qkv = t['qkv'] = self.qkv.fwd(xw)                                           # [Bw*L, 3C] = [Bw][L][3][heads][hd]
         rph, rpw = blk.attn.rel_pos_h.detach(), blk.attn.rel_pos_w.detach()
         assert rph.shape[0] == 2 * Sh - 1 and rpw.shape[0] == 2 * Sw - 1, 'rel-pos interpolation is not implemented'
-        qe, ke = ops.relpos_build(qkv, rph, rpw, Bw, self.heads, hd, Sh, Sw, self.scale)
+        t['rp_aux'] = {}
+        qe, ke = ops.relpos_build(qkv, rph, rpw, Bw, self.heads, hd, Sh, Sw, self.scale, aux=t['rp_aux'])
         v = qkv.view(Bw, L, 3, self.heads, hd)[:, :, 2].permute(0, 2, 1, 3)         # strided view, no copy
         att = torch.empty(Bw * L, C, device=x.device, dtype=torch.bfloat16)
         out_view = att.view(Bw, L, self.heads, hd).permute(0, 2, 1, 3)
@@ -107,7 +108,8 @@ class _Block:
         hbuf, hacc = sink.begin(rph)
         wbuf, wacc = sink.begin(rpw)
         assert hacc == wacc
-        ops.relpos_bwd(dqe, qkv, rph.detach(), rpw.detach(), dqkv, hbuf, wbuf, Bw, self.heads, hd, Sh, Sw, self.scale, accumulate=hacc)
+        ops.relpos_bwd(dqe, qkv, rph.detach(), rpw.detach(), dqkv, hbuf, wbuf, Bw, self.heads, hd, Sh, Sw, self.scale, accumulate=hacc,
+                       aux=t.get('rp_aux'))
         sink.done(rph, hbuf)
         sink.done(rpw, wbuf)
         dxw = self.qkv.bwd(dqkv, t['xw'], sink)

@@ -567,28 +567,51 @@ def relpos_dqk(hd, sh, sw):
     return (hd + sh + sw + 15) // 16 * 16
 
 
-def relpos_build(qkv, rel_pos_h, rel_pos_w, bw, heads, hd, sh, sw, scale):
-    """qkv bf16 [bw, sh*sw, 3*heads*hd] -> (qe, ke) bf16 [bw, heads, sh*sw, dqk] for attn_fwd(scale=1)."""
-    dqk = relpos_dqk(hd, sh, sw)
-    qe = torch.empty(bw, heads, sh * sw, dqk, device=qkv.device, dtype=torch.bfloat16)
+def relpos_nip(sh, sw):
+    return (2 * sh - 1 + 2 * sw - 1 + 63) // 64 * 64
+
+
+def relpos_build(qkv, rel_pos_h, rel_pos_w, bw, heads, hd, sh, sw, scale, aux=None):
+    """qkv bf16 [bw, sh*sw, 3*heads*hd] -> (qe, ke) bf16 [bw, heads, sh*sw, dqk] for attn_fwd(scale=1): the decomposed
+    rel-pos bias q . R_h[qh - kh] + q . R_w[qw - kw] as extra score columns.  The dot products are ONE GEMM of the
+    tensor-core engine (T = qc rtab^T); `aux` (a dict) receives qc and rtab for relpos_bwd."""
+    dqk, nip = relpos_dqk(hd, sh, sw), relpos_nip(sh, sw)
+    rows = bw * heads * sh * sw
+    dev = qkv.device
+    qc = torch.empty(rows, hd, device=dev, dtype=torch.bfloat16)
+    _lib.call('saicv_relpos_pack_q', _p(qkv), _p(qc), bw, heads, hd, sh * sw, _stream())
+    rtab = torch.empty(nip, hd, device=dev, dtype=torch.bfloat16)
+    _lib.call('saicv_relpos_table', _p(rel_pos_h), _p(rel_pos_w), _p(rtab), sh, sw, nip, hd, _stream())
+    t = linear_fwd(qc, rtab)                                   # [rows, nip] bf16
+    qe = torch.empty(bw, heads, sh * sw, dqk, device=dev, dtype=torch.bfloat16)
     ke = torch.empty_like(qe)
-    _lib.call('saicv_relpos_build', _p(qkv), _p(rel_pos_h), _p(rel_pos_w), _p(qe), _p(ke), bw, heads, hd, sh, sw, dqk, scale, _stream())
+    _lib.call('saicv_relpos_gather', _p(qkv), _p(t), _p(qe), _p(ke), bw, heads, hd, sh, sw, dqk, nip, scale, _stream())
+    if aux is not None:
+        aux['qc'], aux['rtab'] = qc, rtab
     return qe, ke
 
 
-def relpos_bwd(dqe, qkv, rel_pos_h, rel_pos_w, dqkv, d_rel_pos_h, d_rel_pos_w, bw, heads, hd, sh, sw, scale, accumulate=False):
-    """dq (from the score-operand gradient dqe) into the q slot of dqkv, and the gradients of the two rel-pos tables as
-    ONE weight-gradient GEMM of the tensor-core engine: [d rel_pos_h ; d rel_pos_w] = ef^T qc (include/saicv_b200.h)."""
-    dqk = dqe.shape[-1]
+def relpos_bwd(dqe, qkv, rel_pos_h, rel_pos_w, dqkv, d_rel_pos_h, d_rel_pos_w, bw, heads, hd, sh, sw, scale, accumulate=False, aux=None):
+    """From the score-operand gradient dqe: dq into the q slot of dqkv and the gradients of the two rel-pos tables.  Both
+    are GEMMs of the tensor-core engine on the re-indexed bias-column gradients ef (include/saicv_b200.h):
+    dq = scale * dqe[:, :hd] + ef rtab,  [d rel_pos_h ; d rel_pos_w] = ef^T qc."""
+    dqk, nip = dqe.shape[-1], relpos_nip(sh, sw)
     rows = bw * heads * sh * sw
     nh, nw = 2 * sh - 1, 2 * sw - 1
-    nip = (nh + nw + 63) // 64 * 64
-    ef = torch.empty(rows, nip, device=dqe.device, dtype=torch.bfloat16)
-    qc = torch.empty(rows, hd, device=dqe.device, dtype=torch.bfloat16)
-    _lib.call('saicv_relpos_bwd', _p(dqe), _p(qkv), _p(rel_pos_h), _p(rel_pos_w), _p(dqkv), _p(ef), _p(qc), nip,
-              bw, heads, hd, sh, sw, dqk, scale, _stream())
-    part = linear_wgrad(ef, qc)                      # [splits, nip, hd]
-    tables = torch.empty(nip, hd, device=dqe.device, dtype=torch.float32)
+    dev = dqe.device
+    if aux is not None and 'qc' in aux:
+        qc, rtab = aux['qc'], aux['rtab']
+    else:
+        qc = torch.empty(rows, hd, device=dev, dtype=torch.bfloat16)
+        _lib.call('saicv_relpos_pack_q', _p(qkv), _p(qc), bw, heads, hd, sh * sw, _stream())
+        rtab = torch.empty(nip, hd, device=dev, dtype=torch.bfloat16)
+        _lib.call('saicv_relpos_table', _p(rel_pos_h), _p(rel_pos_w), _p(rtab), sh, sw, nip, hd, _stream())
+    ef = torch.empty(rows, nip, device=dev, dtype=torch.bfloat16)
+    _lib.call('saicv_relpos_shift', _p(dqe), _p(ef), bw, heads, hd, sh, sw, dqk, nip, _stream())
+    dqx = linear_dgrad(ef, rtab, out_f32=True)                 # [rows, hd] fp32
+    _lib.call('saicv_relpos_dq_combine', _p(dqe), _p(dqx), _p(dqkv), bw, heads, hd, sh * sw, dqk, scale, _stream())
+    part = linear_wgrad(ef, qc)                                # [splits, nip, hd]
+    tables = torch.empty(nip, hd, device=dev, dtype=torch.float32)
     reduce_partials(part, tables)
     reduce_partials(tables[:nh].view(1, nh, hd), d_rel_pos_h, accumulate=accumulate)
     reduce_partials(tables[nh:nh + nw].view(1, nw, hd), d_rel_pos_w, accumulate=accumulate)

@@ -84,28 +84,27 @@ def train_classification(train_loader, model, criterion, optimizer, scheduler, e
     return losses.avg * accum
 
 
-def train_detection(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config):
-    """One epoch of detection training with the reference's step semantics (tools/scripts.py:900-1092): DETR batches carry
-    'image', 'scaled_annots' and 'mask'; the criterion returns a dict of loss terms whose sum is differentiated; NaN / inf
-    / zero-loss guards skip the batch on every rank; gradient accumulation under no_sync(); clipping; per-iteration LR.
+def train_epoch_with_loss_terms(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config, compute,
+                                total_name='total_loss'):
+    """Shared epoch body of the reference's dict-loss training loops (train_detection, tools/scripts.py:900-1092;
+    train_distill_sam_encoder, tools/interactive_segmentation_scripts.py:21-199): `compute(data)` runs the model and the
+    criterion on one device-resident batch and returns (dict of loss terms, tensors to check for inf / nan, batch size).
+    NaN / inf / zero-loss guards skip the batch on every rank; accumulation under no_sync(); clipping; per-iteration LR.
     The reference all-reduces the skip flag, every loss term and the total with one host sync each (>= 20 per step for
     DETR's 18 terms); here they travel in ONE coalesced all-reduce and are read with one sync."""
     losses = AverageMeter()
-    model.train()
     accum = config.accumulation_steps
     assert accum >= 1, 'illegal accumulation_steps!'
     iters = len(train_loader.dataset) // config.batch_size
     group = getattr(config, 'group', None)
     world = _world()
-    is_detr = 'detr' in config.network
     iter_index = 1
     from .utils import CudaPrefetcher
     for _, data in enumerate(CudaPrefetcher(train_loader)):
-        images = data['image']
-        targets = data['scaled_annots'] if is_detr else data['annots']
-        bad = (~torch.isfinite(images)).any() | (~torch.isfinite(targets)).any()
-        outs = model(images, data['mask']) if is_detr else model(images)
-        loss_value = criterion(outs, targets)
+        loss_value, checked, batch = compute(data)
+        bad = torch.zeros((), dtype=torch.bool, device=next(iter(loss_value.values())).device)
+        for t in checked:
+            bad = bad | (~torch.isfinite(t)).any()
         names = list(loss_value)
         terms = torch.stack([loss_value[k].float() for k in names])
         loss = terms.sum()
@@ -139,15 +138,30 @@ def train_detection(train_loader, model, criterion, optimizer, scheduler, epoch,
             optimizer.zero_grad()
             if getattr(config, 'use_ema_model', False):
                 config.ema_model.update(model)
-            losses.update(loss_sum / world, images.size(0))
+            losses.update(loss_sum / world, batch)
             scheduler.step(optimizer, iter_index / iters + (epoch - 1))
         if iter_index % int(config.print_interval * accum) == 0 and _is_master(config):
             msg = (f'train: epoch {epoch:0>4d}, iter [{iter_index // accum:0>5d}, {iters // accum:0>5d}], lr: {scheduler.current_lr:.6f}, '
-                   f'total_loss: {loss_sum / world * accum:.4f}, ')
+                   f'{total_name}: {loss_sum / world * accum:.4f}, ')
             msg += ''.join(f'{k}: {v / world * accum:.4f}, ' for k, v in zip(names, term_sums))
             logger.info(msg)
         iter_index += 1
     return losses.avg * accum
+
+
+def train_detection(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config):
+    """One epoch of detection training with the reference's step semantics (tools/scripts.py:900-1092): DETR batches carry
+    'image', 'scaled_annots' and 'mask'; the criterion returns a dict of loss terms whose sum is differentiated."""
+    model.train()
+    is_detr = 'detr' in config.network
+
+    def compute(data):
+        images = data['image']
+        targets = data['scaled_annots'] if is_detr else data['annots']
+        outs = model(images, data['mask']) if is_detr else model(images)
+        return criterion(outs, targets), (images, targets), images.size(0)
+
+    return train_epoch_with_loss_terms(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config, compute)
 
 
 @torch.no_grad()

@@ -165,3 +165,62 @@ def test_meters_and_amp_type_match_reference():
     assert (m.acc1, m.acc5) == (0.4, 0.8) and (rm is None or (m.acc1, m.acc5) == (rm.acc1, rm.acc5))
     assert "'B200'" in inspect.getsource(common.get_amp_type)
     assert common.get_amp_type(torch.nn.Linear(2, 2)) == torch.bfloat16
+
+
+def test_dict_loss_epoch_body_guards_accumulation_and_schedule(monkeypatch):
+    """train_epoch_with_loss_terms (the body of train_detection / train_distill_sam_encoder): NaN batches are skipped
+    without an optimizer step, gradients accumulate over `accumulation_steps` micro-batches, the scheduler advances once
+    per optimizer step with the reference's epoch fraction, and the returned average is the mean total loss
+    (reference tools/scripts.py:900-1092).  Host logic only: a torch Linear on CPU stands in for the model."""
+    import logging
+    from simpleaicv_pytorch_training_examples_b200.tools import scripts, utils as tutils
+    monkeypatch.setattr(tutils, 'CudaPrefetcher', lambda loader: loader)
+    torch.manual_seed(0)
+    model = torch.nn.Linear(4, 2)
+    ref = torch.nn.Linear(4, 2)
+    ref.load_state_dict(model.state_dict())
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(1)
+    batches = [{'image': torch.randn(3, 4, generator=g), 'target': torch.randn(3, 2, generator=g)} for _ in range(6)]
+    batches[2]['image'][0, 0] = float('nan')
+
+    class Loader(list):
+        dataset = list(range(18))
+
+    class Cfg:
+        accumulation_steps, batch_size, print_interval, local_rank, network = 2, 3, 1, 0, 'resnet50_detr'
+
+    class Sched:
+        current_lr, calls = 0.1, []
+
+        def step(self, optimizer, epoch):
+            self.calls.append(epoch)
+
+    def crit(out, tgt):
+        d = out - tgt
+        return {'a_loss': d.square().mean(), 'b_loss': d.abs().mean()}
+
+    def compute(data):
+        return crit(model(data['image']), data['target']), (data['image'], data['target']), data['image'].size(0)
+
+    sched = Sched()
+    avg = scripts.train_epoch_with_loss_terms(Loader(batches), model, crit, opt, sched, 3, logging.getLogger('t'), Cfg, compute)
+    # straightforward restatement of the reference semantics
+    totals, it = [], 1
+    for b in batches:
+        if not torch.isfinite(b['image']).all():
+            ropt.zero_grad()
+            continue                      # note: the reference `continue`s before iter_index += 1
+        loss = sum(crit(ref(b['image']), b['target']).values()) / 2
+        loss.backward()
+        if it % 2 == 0:
+            ropt.step()
+            ropt.zero_grad()
+            totals.append(float(loss))
+        it += 1
+    for p, q in zip(model.parameters(), ref.parameters()):
+        torch.testing.assert_close(p, q)
+    assert len(sched.calls) == len(totals) == 2
+    assert sched.calls == [2 / 6 + 2, 4 / 6 + 2]
+    assert abs(avg - 2 * sum(totals) / len(totals)) < 1e-6
