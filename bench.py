@@ -30,14 +30,17 @@ import torch.distributed as dist  # noqa: E402
 
 METRICS = {'resnet50': 'images/sec (ResNet-50 224x224 training step, whole job)',
            'vit_base_patch16': 'images/sec (ViT-B/16 224x224 training step, whole job)',
-           'sam_h_encoder': 'images/sec (SAM ViT-H image encoder 1024x1024 training step, whole job)'}
+           'sam_h_encoder': 'images/sec (SAM ViT-H image encoder 1024x1024 training step, whole job)',
+           'resnet50_detr': 'images/sec (DETR-R50 1024x1024 training step, whole job)'}
 WORKLOADS = {'resnet50': 'ResNet-50 224x224 bs256/GPU training step (fwd+CELoss+bwd+grad all-reduce+SGD)',
              'vit_base_patch16': 'ViT-B/16 224x224 bs256/GPU training step (fwd+OneHotLabelCELoss+bwd+grad all-reduce+AdamW)',
              'sam_h_encoder': ('SAM ViT-H image encoder 1024x1024 bs8/GPU training step (encoder fwd + feature MSE against a synthetic '
                                'teacher map, the train_distill_sam_encoder step body + bwd + grad all-reduce + AdamW); prompt encoder / '
-                               'mask decoder are outside the built path')}
-FWD_FLOPS = {'resnet50': 8.178e9, 'vit_base_patch16': 35.13e9, 'sam_h_encoder': 5961e9}   # per image forward; a step is 3x
-ALGO_BYTES = {'resnet50': 130e6, 'vit_base_patch16': 3 * 65e6, 'sam_h_encoder': 3 * 3.1e9}  # per image per step, activations once each way (8d)
+                               'mask decoder are outside the built path'),
+             'resnet50_detr': ('DETR-R50 1024x1024 bs4/GPU training step (the shipped res50_detr_yoloresize1024 shape; fwd + DETRLoss with the '
+                               'Hungarian matcher on the host + bwd + grad all-reduce + AdamW; dropout 0.1 as in the reference constructor)')}
+FWD_FLOPS = {'resnet50': 8.178e9, 'vit_base_patch16': 35.13e9, 'sam_h_encoder': 5961e9, 'resnet50_detr': 191.6e9}   # per image forward; a step is 3x
+ALGO_BYTES = {'resnet50': 130e6, 'vit_base_patch16': 3 * 65e6, 'sam_h_encoder': 3 * 3.1e9, 'resnet50_detr': 130e6 * 20.9}  # per image per step, activations once each way (8d)
 
 
 def _peaks():
@@ -117,6 +120,11 @@ def r50_optimizer_cfg():
 
 def synthetic_batch(model_name, B, rank, pin):
     g = torch.Generator().manual_seed(1234 + rank)
+    if model_name == 'resnet50_detr':   # images + [B, 8, 5] boxes (cx, cy, w, h, class) normalised, no padding rows
+        x = torch.randn(B, 3, 1024, 1024, generator=g)
+        y = torch.cat([torch.rand(B, 8, 2, generator=g) * 0.6 + 0.2, torch.rand(B, 8, 2, generator=g) * 0.3 + 0.05,
+                       torch.randint(0, 80, (B, 8, 1), generator=g).float()], dim=2)
+        return (x.pin_memory(), y.pin_memory()) if pin else (x, y)
     if model_name == 'sam_h_encoder':   # student image + teacher feature map (train_distill_sam_encoder's tensors)
         x = torch.randn(B, 3, 1024, 1024, generator=g)
         y = torch.randn(B, 256, 64, 64, generator=g)
@@ -362,6 +370,7 @@ def roofline_from_table(table, peaks, model_name, B, ms_step, dump_path=None):
     roof = {'bound': dom, 'achieved': d['achieved'] * frac_all / d['frac'] if d and d['frac'] else None, 'peak': d['peak'] if d else None,
             'unit': d['unit'] if d else None, 'frac': frac_all,
             'traffic': (tr or {}).get(model_name, {}).get('dram_bytes_per_launch'),
+            'algorithmic_bytes_per_launch': (sum(v['bytes'] for v in gemm.values()) / max(1, sum(v['calls'] for v in gemm.values()))) if gemm else None,
             'traffic_note': (tr or {}).get(model_name, {}).get('note'),
             'kernel': 'gemm_sm100_kernel (+ attention kernels for ViT)',
             'frac_definition': ('ALL launches of the tensor-core engine in one step: each launch is bounded by max(algorithmic '
@@ -396,10 +405,33 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
     from simpleaicv_pytorch_training_examples_b200.distributed import B200DataParallel, overlap_self_check
     from simpleaicv_pytorch_training_examples_b200.tools import utils as tutils
     dev = torch.device('cuda', local_rank)
-    B = args.batch if model_name != 'sam_h_encoder' else 8
+    B = {'sam_h_encoder': 8, 'resnet50_detr': 4}.get(model_name, args.batch)
     torch.manual_seed(0)
     x_host, y_host = synthetic_batch(model_name, B, rank, True)
-    if model_name == 'sam_h_encoder':
+    detr_masks = None
+    if model_name == 'resnet50_detr':
+        from simpleaicv_pytorch_training_examples_b200.detection import models as det_models
+        from simpleaicv_pytorch_training_examples_b200.detection.losses import DETRLoss
+        model = det_models.resnet50_detr(num_classes=80).to(dev).train()
+        detr_crit = DETRLoss().to(dev)
+        detr_masks = torch.zeros(B, 1024, 1024, dtype=torch.bool, device=dev)
+        detr_masks[:, :, 896:] = True                              # a padded right border, as the collater produces
+
+        class _DetrNet(torch.nn.Module):                           # (images) -> outputs, so that the generic step applies
+            def __init__(self, m):
+                super().__init__()
+                self.m = m
+
+            def forward(self, x):
+                return self.m(x, detr_masks)
+
+        def crit(outs, y):
+            return sum(detr_crit(outs, y).values())
+
+        class _Cfg:
+            optimizer = ('AdamW', {'lr': 1e-4, 'global_weight_decay': False, 'weight_decay': 1e-4, 'no_weight_decay_layer_name_list': []})
+        opt, _ = tutils.build_optimizer(_Cfg, model)
+    elif model_name == 'sam_h_encoder':
         from simpleaicv_pytorch_training_examples_b200.interactive_segmentation.models.segment_anything import sam
         model = sam.sam_h(image_size=1024, use_gradient_checkpoint=False).image_encoder.to(dev).train()
         crit = torch.nn.MSELoss().to(dev)
@@ -416,7 +448,10 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
         model = backbones.vit_base_patch16(image_size=224, num_classes=1000, drop_path_prob=0.1, global_pool=True).to(dev).train()
         crit = losses.OneHotLabelCELoss().to(dev)
         opt, _ = tutils.build_optimizer(vit_optimizer_cfg(model, capturable=(world == 1 or not args.no_graph_ddp)), model)
-    net = B200DataParallel(model) if world > 1 else model
+    ddp = B200DataParallel(model) if world > 1 else None
+    net = ddp if ddp is not None else model
+    if detr_masks is not None:
+        net = _DetrNet(net)
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
     def step(x, y):
@@ -454,7 +489,7 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
         def fb():
             torch.manual_seed(77)
             crit(net(x_dev), y_dev).backward()
-        ndiff = torch.tensor([overlap_self_check(net, fb)], device=dev)
+        ndiff = torch.tensor([overlap_self_check(ddp, fb)], device=dev)
         dist.all_reduce(ndiff, op=dist.ReduceOp.SUM)
         ddp_check = 'ok: overlapped all-reduce bit-identical to no_sync+reduce_now on every rank' if int(ndiff) == 0 \
             else f'FAILED: {int(ndiff)} gradient elements differ'
@@ -463,6 +498,7 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
     if rank == 0:
         sampler.start()
     steps = args.steps if model_name != 'sam_h_encoder' else max(3, args.steps // 3)
+    capturable_step = detr_masks is None     # DETRLoss matches on the host (a sync per step) and DETR trains with dropout
     l0 = _lib.launch_count()
     ms_total = timed(lambda: step(x_dev, y_dev), steps)
     launches = (_lib.launch_count() - l0) * args.steps // steps
@@ -474,7 +510,7 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
     # At N = 1 the step is replayed from ONE CUDA graph (graph.GraphedTrainStep, part of the package's API): the host
     # reads every step's loss, so without the graph the ~600 C-ABI launches of the next step could not be issued ahead.
     graphed, graph_note = None, 'eager launches'
-    if (world == 1 or not args.no_graph_ddp) and not args.no_graph:
+    if (world == 1 or not args.no_graph_ddp) and not args.no_graph and capturable_step:
         try:
             torch.cuda.empty_cache()
             from simpleaicv_pytorch_training_examples_b200.graph import GraphedTrainStep
@@ -518,7 +554,7 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
         # (rank 0 only: the gradient exchange is skipped, otherwise the other ranks would be waited for)
         t = OpTimer()
         t.install()
-        with (net.no_sync() if world > 1 else contextlib.nullcontext()):
+        with (ddp.no_sync() if world > 1 else contextlib.nullcontext()):
             for _ in range(2):
                 step(x_dev, y_dev)
         table = t.summarize()
@@ -555,6 +591,10 @@ def run_b200(args, rank, world, local_rank):
     if args.sam:
         sam_rec = measure_model('sam_h_encoder', args, rank, world, local_rank,
                                 args.dump_ops.replace('.csv', '_sam_h_encoder.csv') if args.dump_ops else None)
+    detr_rec = None
+    if args.detr:
+        detr_rec = measure_model('resnet50_detr', args, rank, world, local_rank,
+                                 args.dump_ops.replace('.csv', '_resnet50_detr.csv') if args.dump_ops else None)
     if rank != 0:
         return
     cpu_base = None
@@ -584,6 +624,9 @@ def run_b200(args, rank, world, local_rank):
     if sam_rec is not None:
         line['sam_h_encoder'] = {k: sam_rec[k] for k in SUB}
         line['sam_h_encoder']['images_per_sec_per_gpu'] = sam_rec['value'] / world
+    if detr_rec is not None:
+        line['resnet50_detr'] = {k: detr_rec[k] for k in SUB}
+        line['resnet50_detr']['images_per_sec_per_gpu'] = detr_rec['value'] / world
     torch_base = os.path.join(ROOT, 'profiles', 'r02_torch_gpu_baseline.json')
     if os.path.exists(torch_base):
         line['torch_ddp_target'] = {'source': 'profiles/r02_torch_gpu_baseline.json (unmodified reference under torch DDP, same pool)',
@@ -603,6 +646,7 @@ def main():
     ap.add_argument('--dump-ops', default=None, help='write the per-op timing table (csv) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-second-model', action='store_true', help='skip the sub-record of the other BASELINE model')
+    ap.add_argument('--detr', action='store_true', help='add the DETR-R50 sub-record (BASELINE configs[4]; shipped 1024x1024 shape, bs4)')
     ap.add_argument('--sam', action='store_true', help='add the SAM ViT-H image-encoder sub-record (BASELINE configs[3]: bs8, 1024x1024)')
     ap.add_argument('--no-graph-ddp', action='store_true',
                     help='N > 1: launch the step eagerly instead of capturing it (NCCL bucket all-reduces included) in one CUDA graph')
