@@ -97,7 +97,10 @@ int saicv_cast_bf16(const float* src, void* dst, long long n, void* stream);
 int saicv_nchw_to_nhwc_bf16(const float* x, void* y, int n, int c, int h, int w, void* stream);
 /* NCHW fp32 image batch -> im2col matrix [n*p*q][kpad] bf16 for the 3-channel stem conv
  * (resnet.py:173-180 7x7/2, resnetforcifar.py:38-45 3x3/1; vit.py:31-37 16x16/16 patches);
- * column (ch*R+r)*S + s. */
+ * column (ch*R+r)*S8 + s with S8 = S rounded up to a multiple of 8 (every filter row is a whole number of 16-byte
+ * vectors; padding columns are zero).  kpad = saicv_stem_kpad(c, r, s) = c*r*S8 rounded up to 64; the weight operand
+ * uses the same column order (saicv_prep_conv_weight / saicv_finish_conv_wgrad with order 1). */
+int saicv_stem_kpad(int c, int r, int s);
 int saicv_stem_im2col(const float* x, void* cols, int n, int c, int h, int w, int r, int s,
                       int stride, int pad, int kpad, void* stream);
 /* u[n, 2p, 2q, c] = dy[n,p,q,c], zero elsewhere; u is [n,h,w,c]. */
@@ -344,6 +347,20 @@ int saicv_heads_pack(const void* src, int ld, int col0, const float* extra, floa
                      int l, int h, int hd, int dp, float scale, void* stream);
 int saicv_heads_unpack(const void* src, void* dst, int ld, int col0, int b, int l, int h, int hd, int dp, float scale,
                        void* stream);
+
+/* ---- SAMLoss on full-resolution mask logits (interactive_segmentation/losses.py:11-198; csrc/capi_loss.cu) ------------
+ * logits: fp32 or bf16 [b][m][n] (n = H*W pixels, n %% 4 == 0); targets: fp32 [b][n] (one plane per image, shared by its
+ * m masks).  sums: fp32 [b*m][6] = { sum focal_weight*bce, sum sigmoid(x)*t, sum sigmoid(x), sum t,
+ * #(x > thr & t > thr), #(x > thr | t > thr) } — everything focal_loss (:126-146), dice_loss (:148-170) and
+ * iou_predict_loss (:172-198) reduce over the pixels, in ONE pass.  partials: fp32 workspace of
+ * saicv_sam_loss_partial_floats(b, m, n) floats (per-block partial sums, folded in a fixed order).
+ * Backward: dlogits[b][m][i] = coef[p][0] * d(focal_weight*bce)/dx + sigmoid'(x) * (coef[p][1] * t + coef[p][2]),
+ * p = b*m_count + m; coef fp32 [b*m][3] (upstream gradients folded with 1/(n b) and the dice quotient rule). */
+int saicv_sam_loss_partial_floats(int b, int m, long long n);
+int saicv_sam_loss_sums(const void* logits, int logits_bf16, const float* targets, float* partials, float* sums, int b,
+                        int m, long long n, float alpha, float gamma, float mask_threshold, void* stream);
+int saicv_sam_loss_bwd(const void* logits, int logits_bf16, const float* targets, const float* coef, void* dlogits,
+                       int dl_bf16, int b, int m, long long n, float alpha, float gamma, void* stream);
 
 #ifdef __cplusplus
 }

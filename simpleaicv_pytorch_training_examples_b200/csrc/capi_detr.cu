@@ -146,12 +146,20 @@ postln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
 
 __global__ void postln_fold_kernel(const float* __restrict__ partials, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                    int nblk, int C, int accumulate) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2C-1
-  if (j >= 2 * C) return;
+  __shared__ float sm[32][9];                            // 8 columns x 32 row groups per block, fixed summation order
+  const int cl = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  const int j = blockIdx.x * 8 + cl;  // 0 .. 2C-1
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partials[(long long)b * 2 * C + j];
+  if (j < 2 * C)
+    for (int b = grp; b < nblk; b += 32) s += partials[(long long)b * 2 * C + j];
+  sm[grp][cl] = s;
+  __syncthreads();
+  if (grp != 0 || j >= 2 * C) return;
+  float t = 0.f;
+#pragma unroll
+  for (int g = 0; g < 32; ++g) t += sm[g][cl];
   float* dst = j < C ? dgamma + j : dbeta + (j - C);
-  *dst = accumulate ? *dst + s : s;
+  *dst = accumulate ? *dst + t : t;
 }
 
 // xb = bf16(x); xpb = bf16(x + pos[row % pos_rows])   (4 columns per thread)
@@ -308,7 +316,7 @@ int saicv_postln_bwd(const float* dy, const float* z, const float* gamma, const 
     default: return set_error("saicv_postln_bwd: unsupported width %d", c);
   }
   if (int e = check_launch("postln_bwd_kernel")) return e;
-  postln_fold_kernel<<<(2 * c + 127) / 128, 128, 0, ST>>>(partials, dgamma, dbeta, grid, c, accumulate);
+  postln_fold_kernel<<<(2 * c + 7) / 8, 256, 0, ST>>>(partials, dgamma, dbeta, grid, c, accumulate);
   return check_launch("postln_fold_kernel");
 }
 

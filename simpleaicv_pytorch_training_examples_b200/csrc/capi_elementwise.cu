@@ -467,6 +467,14 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
        i += (long long)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i]);
 }
+// 8 elements per thread: two 16-byte loads, one 16-byte store (both pointers 16-byte aligned, n8 = n / 8)
+__global__ void cast_bf16_vec_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    dst[i] = pack8(f).q;
+  }
+}
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits,
                                        long long n, int accumulate) {
@@ -477,10 +485,24 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, float*
     out[i] = s;
   }
 }
+// float4 variant (same summation order per element): n4 = n / 4, all pointers 16-byte aligned
+__global__ void reduce_partials_vec_kernel(const float4* __restrict__ partial, float4* __restrict__ out, int splits, long long n4,
+                                           int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 s = accumulate ? out[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < splits; ++k) {
+      const float4 v = __ldg(partial + (long long)k * n4 + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    out[i] = s;
+  }
+}
 
 // order 0: column (r*S+s)*Cp + c (implicit-GEMM convs, Cp = channels padded to the GEMM granule);
-// order 1: column (c*R+r)*S + s (= torch layout, used by the explicit im2col of 3-channel stems /
-// patch embeddings).  Rows k >= K and channels c >= C are zero (channel padding).
+// order 1: column (c*R+r)*S8 + s with S8 = S rounded up to a multiple of 8 (torch order with every filter row padded
+// to whole 16-byte vectors; used by the explicit im2col of 3-channel stems / patch embeddings).  Rows k >= K, channels
+// c >= C and the padding columns are zero.
 __global__ void prep_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int K, int C,
                                         int R, int S, int kpad, int order, int Kp, int Cp) {
   const long long total = (long long)Kp * kpad;
@@ -489,8 +511,10 @@ __global__ void prep_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
     const int k = (int)(i / kpad), j = (int)(i % kpad);
     float v = 0.f;
     if (k < K) {
-      if (order == 1) {
-        if (j < R * S * C) v = w[(long long)k * C * R * S + j];
+      if (order == 1) {               // column (c*R + r)*S8 + s, S8 = S rounded up to 8 (matches stem_im2col_kernel)
+        const int S8 = (S + 7) & ~7;
+        const int cr = j / S8, sx = j % S8;
+        if (cr < C * R && sx < S) v = w[(long long)k * C * R * S + (long long)cr * S + sx];
       } else if (j < R * S * Cp) {
         const int tap = j / Cp, c = j % Cp;
         if (c < C) v = w[((long long)k * C + c) * (R * S) + tap];
@@ -509,7 +533,8 @@ __global__ void finish_conv_wgrad_kernel(const float* __restrict__ partial, floa
     const int tap = (int)(i % (R * S));
     const long long kc = i / (R * S);
     const int c = (int)(kc % C), k = (int)(kc / C);
-    const long long src = order == 1 ? (long long)k * kpad + (i - (long long)k * C * R * S)
+    const int S8 = (S + 7) & ~7;
+    const long long src = order == 1 ? (long long)k * kpad + (long long)(c * R + tap / S) * S8 + tap % S
                                      : (long long)k * kpad + (long long)tap * Cp + c;
     float s = accumulate ? grad[i] : 0.f;
     for (int sp = 0; sp < splits; ++sp) s += partial[(long long)sp * Kp * kpad + src];
@@ -528,17 +553,17 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
   }
 }
 
-// Explicit im2col for 3-channel inputs (ResNet stems, ViT patch embedding).  One block owns T
-// consecutive output pixels of one output row: the (C, R, (T-1)*stride+S) input patch is staged in
-// shared memory with coalesced loads, then written out as 16-byte bf16 vectors of the row-major
-// [pixels][kpad] matrix, column (c*R+r)*S + s.
+// Explicit im2col for 3-channel inputs (ResNet stems, ViT / SAM / VAN patch embeddings).  One block owns T consecutive
+// output pixels of one output row: the (C, R, (T-1)*stride+S) input patch is staged in shared memory with coalesced
+// loads; every thread then produces whole 16-byte vectors of one (pixel, channel, filter row): column
+// (c*R + r)*S8 + s of the row-major [pixels][kpad] matrix (S8 = S rounded up to 8, padding columns zero), i.e. S
+// consecutive floats of the staged patch per S8/8 output vectors - no per-element index table.
 __global__ void __launch_bounds__(kThreads)
 stem_im2col_kernel(const float* __restrict__ x, void* __restrict__ cols, int N, int C, int H, int W, int R, int S,
                    int stride, int pad, int P, int Q, int kpad, int T) {
   extern __shared__ float sm[];
   const int Wt = (T - 1) * stride + S;
   float* patch = sm;                                      // [C*R][Wt]
-  int* koff = reinterpret_cast<int*>(sm + C * R * Wt);    // [kpad] offset of column k inside `patch`
   const int qtiles = (Q + T - 1) / T;
   const int qt = blockIdx.x % qtiles;
   const int p = (blockIdx.x / qtiles) % P;
@@ -553,18 +578,21 @@ stem_im2col_kernel(const float* __restrict__ x, void* __restrict__ cols, int N, 
     if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(x + (((long long)n * C + c) * H + h) * W + w);
     patch[i] = v;
   }
-  for (int k = threadIdx.x; k < kpad; k += blockDim.x) koff[k] = k < C * R * S ? (k / S) * Wt + (k % S) : -1;
   __syncthreads();
-  const int vpr = kpad >> 3;
+  const int vpr = kpad >> 3, S8 = (S + 7) & ~7, vps = S8 >> 3;   // vectors per matrix row / per filter row
   const int npix = min(T, Q - q0);
   const long long row0 = ((long long)n * P + p) * Q + q0;
   for (int v = threadIdx.x; v < npix * vpr; v += blockDim.x) {
     const int pix = v / vpr, kv = v - pix * vpr;
+    const int cr = kv / vps, s0 = (kv - cr * vps) * 8;
     float f[8];
+    if (cr < C * R) {
+      const float* src = patch + cr * Wt + pix * stride + s0;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int o = koff[kv * 8 + e];
-      f[e] = o >= 0 ? patch[o + pix * stride] : 0.f;
+      for (int e = 0; e < 8; ++e) f[e] = (s0 + e < S) ? src[e] : 0.f;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = 0.f;
     }
     stg8(cols, (row0 + pix) * vpr + kv, pack8(f));
   }
@@ -615,8 +643,12 @@ __global__ void add_strided2_kernel(void* __restrict__ dx, const void* __restric
 // (p*stride - pad, q*stride - pad).  Out-of-range taps are skipped (-inf padding, nn.MaxPool2d) or,
 // with oob_zero, take part with the value 0 (nn.ZeroPad2d followed by an unpadded pool,
 // darknet.py:212-213): their code is 255 and they receive no gradient.  argmax byte = r*K + s.
+// KT > 0: the window size is a compile-time constant, so the K*K window loads are unrolled and all in flight at once
+// (the runtime-K loop issues them one by one: 3.5 TB/s of L1 traffic, 3x off the HBM time of the 3x3/2 stem pool)
+template <int KT>
 __global__ void maxpool_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, uint8_t* __restrict__ amax,
-                                   int N, int H, int W, int C, int P, int Q, int K, int stride, int pad, int oob_zero) {
+                                   int N, int H, int W, int C, int P, int Q, int Krt, int stride, int pad, int oob_zero) {
+  const int K = KT > 0 ? KT : Krt;
   const int vpr = C >> 3;
   const long long total = (long long)N * P * Q * vpr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -631,24 +663,49 @@ __global__ void maxpool_fwd_kernel(const void* __restrict__ x, void* __restrict_
 #pragma unroll
     for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; arg[k] = 0; }
     bool first = true;
-    for (int r = 0; r < K; ++r) {
-      const int h = stride * p - pad + r;
-      for (int s = 0; s < K; ++s) {
-        const int w = stride * q - pad + s;
-        const bool inside = h >= 0 && h < H && w >= 0 && w < W;
-        if (!inside && !oob_zero) continue;
-        float f[8];
-        if (inside) {
-          unpack8(ldg8(x, ((n * H + h) * W + w) * vpr + v), f);
-        } else {
+    if (KT > 0) {
+      V8 win[KT > 0 ? KT * KT : 1];
+      bool ok[KT > 0 ? KT * KT : 1];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] = 0.f;
+      for (int r = 0; r < KT; ++r)
+#pragma unroll
+        for (int s = 0; s < KT; ++s) {
+          const int h = stride * p - pad + r, w = stride * q - pad + s;
+          ok[r * KT + s] = h >= 0 && h < H && w >= 0 && w < W;
+          win[r * KT + s].zero();
+          if (ok[r * KT + s]) win[r * KT + s] = ldg8(x, ((n * H + h) * W + w) * vpr + v);
         }
-        const int code = inside ? r * K + s : 255;
+#pragma unroll
+      for (int t = 0; t < KT * KT; ++t) {
+        if (!ok[t] && !oob_zero) continue;
+        float f[8];
+        unpack8(win[t], f);
+        const int code = ok[t] ? t : 255;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           if (first || f[k] > best[k]) { best[k] = f[k]; arg[k] = code; }
         first = false;
+      }
+    } else {
+      for (int r = 0; r < K; ++r) {
+        const int h = stride * p - pad + r;
+        for (int s = 0; s < K; ++s) {
+          const int w = stride * q - pad + s;
+          const bool inside = h >= 0 && h < H && w >= 0 && w < W;
+          if (!inside && !oob_zero) continue;
+          float f[8];
+          if (inside) {
+            unpack8(ldg8(x, ((n * H + h) * W + w) * vpr + v), f);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = 0.f;
+          }
+          const int code = inside ? r * K + s : 255;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (first || f[k] > best[k]) { best[k] = f[k]; arg[k] = code; }
+          first = false;
+        }
       }
     }
     stg8(y, i, pack8(best));
@@ -659,6 +716,9 @@ __global__ void maxpool_fwd_kernel(const void* __restrict__ x, void* __restrict_
   }
 }
 
+// FAST: K <= 2 * stride, i.e. an input pixel lies in at most 2 x 2 output windows; the four (argmax, dy) pairs are
+// loaded together instead of through two runtime-bounded loops (3x3/2 stem pool: 0.5 ms -> HBM time)
+template <bool FAST>
 __global__ void maxpool_bwd_kernel(const void* __restrict__ dy, const uint8_t* __restrict__ amax,
                                    void* __restrict__ dx, int N, int H, int W, int C, int P, int Q, int K, int stride,
                                    int pad) {
@@ -678,6 +738,35 @@ __global__ void maxpool_bwd_kernel(const void* __restrict__ dy, const uint8_t* _
     const int hp = h + pad, wp = w + pad;
     const int p_hi = min(hp / stride, P - 1), q_hi = min(wp / stride, Q - 1);
     const int p_lo = max((hp - K + stride) / stride, 0), q_lo = max((wp - K + stride) / stride, 0);
+    if (FAST) {
+      uint64_t am[4];
+      V8 gv[4];
+      int code[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int p = hp / stride - (t >> 1), q = wp / stride - (t & 1);
+        const int r = hp - stride * p, s2 = wp - stride * q;
+        const bool ok = p >= 0 && p < P && q >= 0 && q < Q && r < K && s2 < K;
+        code[t] = ok ? r * K + s2 : -1;
+        am[t] = 0;
+        gv[t].zero();
+        if (ok) {
+          const long long oi = ((n * P + p) * Q + q) * vpr + v;
+          am[t] = __ldg(reinterpret_cast<const uint64_t*>(amax) + oi);
+          gv[t] = ldg8(dy, oi);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float g[8];
+        unpack8(gv[t], g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if ((int)((am[t] >> (8 * k)) & 0xff) == code[t]) acc[k] += g[k];
+      }
+      stg8(dx, i, pack8(acc));
+      continue;
+    }
     for (int p = p_lo; p <= p_hi; ++p) {
       const int r = hp - stride * p;
       if (r < 0 || r >= K) continue;
@@ -818,12 +907,21 @@ int saicv_add_bf16(void* a, const void* b, long long n, void* stream) {
 }
 
 int saicv_cast_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (n % 8 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+    cast_bf16_vec_kernel<<<grid_for(n / 8), kThreads, 0, ST>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n / 8);
+    return check_launch("cast_bf16_vec_kernel");
+  }
   cast_bf16_kernel<<<grid_for(n), kThreads, 0, ST>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   return check_launch("cast_bf16_kernel");
 }
 
 int saicv_reduce_partials(const float* partial, float* out, int splits, long long n, int accumulate,
                           void* stream) {
+  if (n % 4 == 0 && ((uintptr_t)partial & 15) == 0 && ((uintptr_t)out & 15) == 0) {
+    reduce_partials_vec_kernel<<<grid_for(n / 4), kThreads, 0, ST>>>(reinterpret_cast<const float4*>(partial), reinterpret_cast<float4*>(out),
+                                                                    splits, n / 4, accumulate);
+    return check_launch("reduce_partials_vec_kernel");
+  }
   reduce_partials_kernel<<<grid_for(n), kThreads, 0, ST>>>(partial, out, splits, n, accumulate);
   return check_launch("reduce_partials_kernel");
 }
@@ -854,13 +952,16 @@ int saicv_nchw_to_nhwc_bf16(const float* x, void* y, int n, int c, int h, int w,
   return check_launch("nchw_to_nhwc_kernel");
 }
 
+int saicv_stem_kpad(int c, int r, int s) { return (c * r * ((s + 7) / 8 * 8) + 63) / 64 * 64; }
+
 int saicv_stem_im2col(const float* x, void* cols, int n, int c, int h, int w, int r, int s, int stride, int pad,
                       int kpad, void* stream) {
-  if (kpad % 8 || kpad < r * s * c) return set_error("saicv_stem_im2col: bad kpad %d", kpad);
+  if (kpad % 8 || kpad < r * c * ((s + 7) / 8 * 8))
+    return set_error("saicv_stem_im2col: kpad %d must be a multiple of 8 >= c*r*roundup(s, 8) = %d (saicv_stem_kpad)", kpad, r * c * ((s + 7) / 8 * 8));
   const int P = (h + 2 * pad - r) / stride + 1, Q = (w + 2 * pad - s) / stride + 1;
   int T = 32;  // output pixels per block; shrink until the staged patch fits in 40 KB
-  while (T > 1 && ((size_t)c * r * ((T - 1) * stride + s) * 4 + (size_t)kpad * 4) > 40 * 1024) T >>= 1;
-  const size_t smem = (size_t)c * r * ((T - 1) * stride + s) * 4 + (size_t)kpad * 4;
+  while (T > 1 && ((size_t)c * r * ((T - 1) * stride + s) * 4) > 40 * 1024) T >>= 1;
+  const size_t smem = (size_t)c * r * ((T - 1) * stride + s) * 4;
   if (smem > 48 * 1024) return set_error("saicv_stem_im2col: patch of %zu bytes does not fit in shared memory", smem);
   const long long blocks = (long long)n * P * ((Q + T - 1) / T);
   stem_im2col_kernel<<<(unsigned)blocks, kThreads, smem, ST>>>(x, cols, n, c, h, w, r, s, stride, pad, P, Q, kpad, T);
@@ -884,8 +985,10 @@ int saicv_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int n, int h, int
   if (c % 8) return set_error("saicv_maxpool_fwd: C %% 8 != 0");
   if (k < 1 || k > 15 || stride < 1) return set_error("saicv_maxpool_fwd: unsupported window %d / stride %d", k, stride);
   const int P = (h + pad + pad_hi - k) / stride + 1, Q = (w + pad + pad_hi - k) / stride + 1;
-  maxpool_fwd_kernel<<<grid_for((long long)n * P * Q * (c / 8)), kThreads, 0, ST>>>(x, y, argmax, n, h, w, c, P, Q, k, stride,
-                                                                                    pad, oob_zero);
+  const int grid = grid_for((long long)n * P * Q * (c / 8));
+  if (k == 3) maxpool_fwd_kernel<3><<<grid, kThreads, 0, ST>>>(x, y, argmax, n, h, w, c, P, Q, k, stride, pad, oob_zero);
+  else if (k == 2) maxpool_fwd_kernel<2><<<grid, kThreads, 0, ST>>>(x, y, argmax, n, h, w, c, P, Q, k, stride, pad, oob_zero);
+  else maxpool_fwd_kernel<0><<<grid, kThreads, 0, ST>>>(x, y, argmax, n, h, w, c, P, Q, k, stride, pad, oob_zero);
   return check_launch("maxpool_fwd_kernel");
 }
 
@@ -893,8 +996,9 @@ int saicv_maxpool_bwd(const void* dy, const uint8_t* argmax, void* dx, int n, in
                       int pad, int pad_hi, void* stream) {
   if (c % 8) return set_error("saicv_maxpool_bwd: C %% 8 != 0");
   const int P = (h + pad + pad_hi - k) / stride + 1, Q = (w + pad + pad_hi - k) / stride + 1;
-  maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8)), kThreads, 0, ST>>>(dy, argmax, dx, n, h, w, c, P, Q, k, stride,
-                                                                                    pad);
+  const int grid = grid_for((long long)n * h * w * (c / 8));
+  if (k <= 2 * stride && k >= stride) maxpool_bwd_kernel<true><<<grid, kThreads, 0, ST>>>(dy, argmax, dx, n, h, w, c, P, Q, k, stride, pad);
+  else maxpool_bwd_kernel<false><<<grid, kThreads, 0, ST>>>(dy, argmax, dx, n, h, w, c, P, Q, k, stride, pad);
   return check_launch("maxpool_bwd_kernel");
 }
 

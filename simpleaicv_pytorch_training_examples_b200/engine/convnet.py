@@ -82,7 +82,7 @@ class ConvBN:
         self.kp = _round_up(k, 64)
         self.cp = c if self.is_stem else _round_up(c, 64)
         self.padded = self.kp != k
-        self.kpad = _round_up(r * s * c, 64) if self.is_stem else r * s * self.cp
+        self.kpad = ops.stem_kpad(c, r, s) if self.is_stem else r * s * self.cp
         self.w_bf16 = None
         self.w_version = None
         self.sums = None

@@ -138,7 +138,7 @@ class SamEncoderRT:
         w = m.patch_embed.proj.weight
         if self._changed('pw', w):
             k = w.shape[1] * w.shape[2] * w.shape[3]
-            self.kpad = (k + 63) // 64 * 64
+            self.kpad = ops.stem_kpad(w.shape[1], w.shape[2], w.shape[3])
             if self.pw_bf16 is None:
                 self.pw_bf16 = torch.empty(w.shape[0], self.kpad, device=w.device, dtype=torch.bfloat16)
             ops.prep_conv_weight(w.detach(), self.pw_bf16, self.kpad, order=ops.ORDER_CRS)

@@ -172,7 +172,7 @@ class _PatchEmbed:
         ver = (w.data_ptr(), w._version)
         if self.w_bf16 is None or ver != self.version:
             k, c = self.k, w.shape[1]
-            self.kpad = (k * k * c + 63) // 64 * 64 if self.from_image else k * k * c
+            self.kpad = ops.stem_kpad(c, k, k) if self.from_image else k * k * c
             if self.w_bf16 is None:
                 self.w_bf16 = torch.empty(w.shape[0], self.kpad, device=w.device, dtype=torch.bfloat16)
             ops.prep_conv_weight(w.detach(), self.w_bf16, self.kpad, order=ops.ORDER_CRS if self.from_image else ops.ORDER_RSC)

@@ -187,7 +187,7 @@ class ViTRT:
         ver = (w.data_ptr(), w._version)
         if self.pw_bf16 is None or ver != self.pw_version:
             k = w.shape[1] * w.shape[2] * w.shape[3]
-            self.kpad = (k + 63) // 64 * 64
+            self.kpad = ops.stem_kpad(w.shape[1], w.shape[2], w.shape[3])
             if self.pw_bf16 is None:
                 self.pw_bf16 = torch.empty(w.shape[0], self.kpad, device=w.device, dtype=torch.bfloat16)
             ops.prep_conv_weight(w.detach(), self.pw_bf16, self.kpad, order=ops.ORDER_CRS)

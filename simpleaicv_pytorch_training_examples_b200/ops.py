@@ -155,6 +155,12 @@ def nchw_to_nhwc_bf16(x, out=None):
     return out
 
 
+def stem_kpad(c, r, s):
+    """Columns of the explicit-im2col matrix / weight operand of a c-channel r x s stem conv (filter rows padded to 8,
+    total rounded up to the 64-wide reduction block)."""
+    return (c * r * ((s + 7) // 8 * 8) + 63) // 64 * 64
+
+
 def stem_im2col(x, r, s, stride, pad, kpad, out=None):
     n, c, h, w = x.shape
     P, Q = conv_out_size(h, pad, r, stride), conv_out_size(w, pad, s, stride)
@@ -674,3 +680,26 @@ def heads_unpack(src, dst, col0, hd, scale=1.0):
     b, h, l, dp = src.shape
     _lib.call('saicv_heads_unpack', _p(src), _p(dst), dst.shape[1], col0, b, l, h, hd, dp, float(scale), _stream())
     return dst
+
+
+# ----------------------------------------------------------------------------- SAMLoss
+def sam_loss_sums(logits, targets, alpha, gamma, mask_threshold):
+    """logits fp32 / bf16 [B, M, H, W], targets fp32 [B, 1, H, W] -> fp32 [B, M, 6] per-mask sums (include/saicv_b200.h)."""
+    b, m = logits.shape[:2]
+    n = logits[0, 0].numel()
+    assert logits.is_contiguous() and targets.is_contiguous() and targets.dtype == torch.float32 and targets.numel() == b * n
+    part = torch.empty(_lib.load().saicv_sam_loss_partial_floats(b, m, n), device=logits.device, dtype=torch.float32)
+    sums = torch.empty(b, m, 6, device=logits.device, dtype=torch.float32)
+    _lib.call('saicv_sam_loss_sums', _p(logits), int(logits.dtype == torch.bfloat16), _p(targets), _p(part), _p(sums), b, m, n,
+              float(alpha), float(gamma), float(mask_threshold), _stream())
+    return sums
+
+
+def sam_loss_bwd(logits, targets, coef, alpha, gamma):
+    """Gradient of the loss w.r.t. the mask logits (dtype of logits) from the per-mask coefficients coef fp32 [B, M, 3]."""
+    b, m = logits.shape[:2]
+    n = logits[0, 0].numel()
+    dl = torch.empty_like(logits)
+    _lib.call('saicv_sam_loss_bwd', _p(logits), int(logits.dtype == torch.bfloat16), _p(targets), _p(coef.contiguous()), _p(dl),
+              int(logits.dtype == torch.bfloat16), b, m, n, float(alpha), float(gamma), _stream())
+    return dl

@@ -179,10 +179,12 @@ def test_conv_wgrad(n, h, w, c, k, r, stride, pad):
     _close(dw, ref, 1e-3, 1e-3, f'conv_wgrad splits={part.shape[0]}')
 
 
-@pytest.mark.parametrize('n,c,h,w,k,r,stride,pad,kpad', [(4, 3, 32, 32, 64, 7, 2, 3, 192), (3, 3, 37, 41, 64, 3, 1, 1, 64),
-                                                       (2, 3, 64, 64, 128, 16, 16, 0, 768), (2, 3, 224, 224, 64, 7, 2, 3, 192)])
+@pytest.mark.parametrize('n,c,h,w,k,r,stride,pad,kpad', [(4, 3, 32, 32, 64, 7, 2, 3, 192), (3, 3, 37, 41, 64, 3, 1, 1, 128),
+                                                       (2, 3, 64, 64, 128, 16, 16, 0, 768), (2, 3, 224, 224, 64, 7, 2, 3, 192),
+                                                       (2, 3, 56, 56, 32, 7, 4, 3, 192)])
 def test_stem_im2col_matches_conv(n, c, h, w, k, r, stride, pad, kpad):
     ops = _ops()
+    assert kpad == ops.stem_kpad(c, r, r)                # filter rows padded to 8 columns, total rounded up to 64
     x = _bf(n, c, h, w, seed=11).float()
     wt = _bf(k, c, r, r, scale=0.1, seed=12).float()
     cols = ops.stem_im2col(x, r, r, stride, pad, kpad)
