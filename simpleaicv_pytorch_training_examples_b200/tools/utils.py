@@ -181,38 +181,64 @@ class CudaPrefetcher:
     of batch i+1 is issued on a side stream before the kernels of step i are enqueued, so PCIe
     traffic overlaps compute (the reference does a blocking ``.cuda()`` per step,
     tools/scripts.py:143).  Yields dicts of device tensors that are safe to use on the current
-    stream."""
+    stream.
+
+    The device tensors live in TWO persistent slots that alternate (allocated on first use, re-allocated
+    only when a batch changes shape): a fresh ``.to(device)`` per batch would go through the caching
+    allocator on the side stream, whose cross-stream reuse rules can turn into cudaMalloc / cudaFree
+    calls (device-wide syncs of several ms) in the middle of the step.  A slot is overwritten only after
+    the consumer has asked for the following batch, i.e. after everything that reads it was enqueued:
+    the side stream waits for an event recorded on the consumer's stream when it comes back for the next
+    batch.  Consequently a yielded batch is valid until the consumer requests the next one (work already
+    enqueued on the consumer's stream still sees the old contents; tensors to keep longer must be cloned)."""
 
     def __init__(self, loader, device=None):
         self.loader = loader
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
         self.stream = torch.cuda.Stream(self.device)
+        self._slots = [{}, {}]
+        self._free = [None, None]      # event after which slot k may be overwritten
 
     def __len__(self):
         return len(self.loader)
 
-    def _issue(self, it):
+    def _issue(self, it, k):
         batch = next(it, None)
         if batch is None:
             return None
+        slot = self._slots[k & 1]
         with torch.cuda.stream(self.stream):
-            out = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            if self._free[k & 1] is not None:
+                self.stream.wait_event(self._free[k & 1])
+            out = {}
+            for name, v in batch.items():
+                if not torch.is_tensor(v):
+                    out[name] = v
+                    continue
+                buf = slot.get(name)
+                if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                    buf = slot[name] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                buf.copy_(v, non_blocking=True)
+                out[name] = buf
             ev = torch.cuda.Event()
             ev.record(self.stream)
         return out, ev
 
     def __iter__(self):
         it = iter(self.loader)
-        nxt = self._issue(it)
+        k = 0
+        nxt = self._issue(it, k)
         while nxt is not None:
             cur, ev = nxt
             main = torch.cuda.current_stream(self.device)
             main.wait_event(ev)
-            for v in cur.values():
-                if torch.is_tensor(v):
-                    v.record_stream(main)
-            nxt = self._issue(it)  # batch i+1 starts copying before step i is enqueued
+            k += 1
+            nxt = self._issue(it, k)  # batch i+1 starts copying before step i is enqueued
             yield cur
+            # the consumer is back: every kernel that reads `cur` has been enqueued on its stream
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+            self._free[(k - 1) & 1] = done
 
 
 def unwrap(model):
