@@ -39,11 +39,11 @@ def test_mask_terms_and_gradients_match_torch(B, M, H, W, dtype, gamma):
     g = torch.Generator().manual_seed(B * 100 + M)
     x = (torch.randn(B, M, H, W, generator=g) * 3).to(dtype)
     t = (torch.rand(B, 1, H, W, generator=g) > 0.6).float()
-    xr = x.float().requires_grad_(True)
+    xr = x.float().clone().requires_grad_(True)
     f_r, d_r, gt_r = _reference_terms(xr, t, 0.25, gamma, 0.)
     wf, wd = torch.randn(B, M, generator=g), torch.randn(B, M, generator=g)
     ((f_r * wf).sum() + (d_r * wd).sum()).backward()
-    xc = x.cuda().requires_grad_(True)
+    xc = x.detach().clone().cuda().requires_grad_(True)
     f, d, gt = _MaskTerms.apply(xc, t.cuda(), 0.25, float(gamma), 0.)
     torch.testing.assert_close(f.cpu(), f_r.detach(), rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(d.cpu(), d_r.detach(), rtol=1e-4, atol=1e-7)
