@@ -294,6 +294,7 @@ typedef struct {
    * over (row (b*h + head)*lq + q, column k) under dropout_seed, recomputed by the backward.  0 = off. */
   float dropout_p;
   unsigned long long dropout_seed;
+  const unsigned long long* dropout_seed_base;  /* device word added to dropout_seed (nullable), see saicv_dropout */
 } saicv_attn_args;
 int saicv_attn_fwd(const saicv_attn_args* a, void* stream);
 /* Backward: fwd holds the forward's arguments (out = the forward output, lse as written by it); dout has the
@@ -336,9 +337,12 @@ int saicv_add_pos_cast(const float* x, const float* pos, long long pos_rows, voi
 /* Dropout with the counter hash of csrc/dropout_hash.cuh over the element index:
  * out = (keep ? in / (1 - p) : 0) * (row_scale ? row_scale[index / elems_per_scale] : 1) (+ resid, fp32, only with an
  * fp32 out).  row_scale is the per-sample drop-path scale of the branch (vit.py:102-135).  in / out are bf16 or fp32
- * (flags); the same call on a gradient with the same seed is the backward pass.  n %% 4 == 0. */
+ * (flags); the same call on a gradient with the same seed is the backward pass.  n %% 4 == 0.  The effective seed is
+ * seed + *seed_base when seed_base (a device pointer) is given: a training step captured in a CUDA graph refreshes the
+ * device word every replay, so the masks change from step to step although `seed` is a constant of the graph. */
 int saicv_dropout(const void* in, int in_f32, const float* resid, const float* row_scale, long long elems_per_scale,
-                  void* out, int out_f32, long long n, float p, unsigned long long seed, void* stream);
+                  void* out, int out_f32, long long n, float p, unsigned long long seed,
+                  const unsigned long long* seed_base, void* stream);
 /* Per-head packing of projected rows into a score operand: dst bf16 [b][h][l][dp],
  * dst[.., 0:hd] = src[(b*l + l') * ld + col0 + head*hd + :] * scale, dst[.., hd] = extra ? extra[b*l + l'] :
  * extra_const (the column that carries nn.MultiheadAttention's additive float key_padding_mask against a constant-1

@@ -29,7 +29,8 @@ class AttnArgs(ctypes.Structure):
                 ('q_strides', c_ll * 3), ('k_strides', c_ll * 3), ('v_strides', c_ll * 3), ('o_strides', c_ll * 3),
                 ('key_mask_bits', c_void_p), ('mask_words', c_int),
                 ('b', c_int), ('h', c_int), ('lq', c_int), ('lk', c_int), ('dqk', c_int), ('dv', c_int),
-                ('scale', c_float), ('dropout_p', c_float), ('dropout_seed', ctypes.c_ulonglong)]
+                ('scale', c_float), ('dropout_p', c_float), ('dropout_seed', ctypes.c_ulonglong),
+                ('dropout_seed_base', c_void_p)]
 
 
 class AttnBwdArgs(ctypes.Structure):
@@ -101,7 +102,7 @@ SIGNATURES = {
     'saicv_postln_fwd': [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     'saicv_postln_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p],
     'saicv_add_pos_cast': [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_void_p],
-    'saicv_dropout': [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_ll, c_float, ctypes.c_ulonglong, c_void_p],
+    'saicv_dropout': [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_ll, c_float, ctypes.c_ulonglong, c_void_p, c_void_p],
     'saicv_heads_pack': [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     'saicv_heads_unpack': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     'saicv_dwconv_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],

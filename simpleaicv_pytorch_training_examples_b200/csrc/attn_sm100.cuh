@@ -29,7 +29,18 @@ constexpr int kAttnThreads = 192;
 struct AttnDrop {            // attention-probability dropout (thresh == 0: off), see dropout_hash.cuh
   uint32_t thresh, seed_lo, seed_hi;
   float scale;                // 1 / (1 - p)
+  const unsigned long long* seed_base;   // device word added to the seed (nullable): fresh masks per CUDA-graph replay
 };
+// the effective seed words of this launch (one uniform global load when a device base is given)
+__device__ __forceinline__ AttnDrop resolve_drop(const AttnDrop& d) {
+  AttnDrop r = d;
+  if (d.thresh != 0 && d.seed_base != nullptr) {
+    const unsigned long long s = (((unsigned long long)d.seed_hi << 32) | d.seed_lo) + *d.seed_base;
+    r.seed_lo = (uint32_t)s;
+    r.seed_hi = (uint32_t)(s >> 32);
+  }
+  return r;
+}
 
 struct AttnParams {
   AttnDrop drop;
@@ -251,6 +262,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     uint8_t* const prow = sP + row * 128;
     const int sw = row & 7;
     const float thr_raw = 8.0f / p.scale_log2;        // raise the reference only past a factor 2^8
+    const AttnDrop drop = DROP ? resolve_drop(p.drop) : p.drop;
     uint32_t g = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int qt = w % p.num_q_tiles, bh = w / p.num_q_tiles, b = bh / p.H, h = bh % p.H;
@@ -316,7 +328,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
               }
             }
             const float msl = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
-            rs = chunk_exp_store<DROP>(v, dead, p.scale_log2, msl, rs, prow + (c >> 1) * 16384, (c & 1) * 4, sw, p.drop,
+            rs = chunk_exp_store<DROP>(v, dead, p.scale_log2, msl, rs, prow + (c >> 1) * 16384, (c & 1) * 4, sw, drop,
                                  (uint32_t)(bh * p.Lq + qt * 128 + row), (uint32_t)(j * BN + c * 32));
           }
         } while (restart);
@@ -544,6 +556,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_con
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int sw = row & 7;
+    const AttnDrop drop = DROP ? resolve_drop(p.drop) : p.drop;
     const int tid = threadIdx.x - 64;
     uint32_t it = 0, g = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
@@ -629,13 +642,13 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_con
                 const int col = j * BN + c * 32 + 8 * t + i;
                 const uint32_t qi = ROWS_ARE_KEYS ? (uint32_t)col : (uint32_t)grow;
                 const uint32_t ki = ROWS_ARE_KEYS ? (uint32_t)grow : (uint32_t)col;
-                const bool keep = dropout_hash(p.drop.seed_lo, p.drop.seed_hi, (uint32_t)bh * (uint32_t)p.Lq + qi, ki) >= p.drop.thresh;
-                const float dpv = keep ? __uint_as_float(dv[c][8 * t + i]) * p.drop.scale : 0.f;
+                const bool keep = dropout_hash(drop.seed_lo, drop.seed_hi, (uint32_t)bh * (uint32_t)p.Lq + qi, ki) >= drop.thresh;
+                const float dpv = keep ? __uint_as_float(dv[c][8 * t + i]) * drop.scale : 0.f;
                 float dlv;
                 if (ROWS_ARE_KEYS) dlv = sLse[64 + c * 32 + 8 * t + i];
                 else dlv = dl_r;
                 ds[i] = pp[i] * (dpv - dlv);
-                pp[i] = keep ? pp[i] * p.drop.scale : 0.f;
+                pp[i] = keep ? pp[i] * drop.scale : 0.f;
               }
             }
             if (dead != 0) {

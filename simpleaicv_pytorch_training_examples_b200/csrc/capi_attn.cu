@@ -97,6 +97,7 @@ AttnDrop make_drop(const saicv_attn_args* a) {
     d.seed_lo = (uint32_t)a->dropout_seed;
     d.seed_hi = (uint32_t)(a->dropout_seed >> 32);
     d.scale = 1.f / (1.f - a->dropout_p);
+    d.seed_base = a->dropout_seed_base;
   }
   return d;
 }

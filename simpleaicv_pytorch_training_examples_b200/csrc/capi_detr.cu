@@ -185,7 +185,9 @@ __global__ void add_pos_cast_kernel(const float* __restrict__ x, const float* __
 template <bool IN_F32, bool OUT_F32>
 __global__ void dropout_kernel(const void* __restrict__ in, const float* __restrict__ resid, const float* __restrict__ row_scale,
                                long long elems_per_scale, void* __restrict__ out, long long n4, uint32_t thresh, float inv_keep,
-                               uint32_t seed_lo, uint32_t seed_hi) {
+                               unsigned long long seed, const unsigned long long* __restrict__ seed_base) {
+  if (seed_base) seed += *seed_base;                 // device-resident base: a captured graph sees a fresh one per replay
+  const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v;
     if (IN_F32) {
@@ -330,18 +332,18 @@ int saicv_add_pos_cast(const float* x, const float* pos, long long pos_rows, voi
 }
 
 int saicv_dropout(const void* in, int in_f32, const float* resid, const float* row_scale, long long elems_per_scale, void* out,
-                  int out_f32, long long n, float p, unsigned long long seed, void* stream) {
+                  int out_f32, long long n, float p, unsigned long long seed, const unsigned long long* seed_base, void* stream) {
   if (row_scale && (elems_per_scale <= 0 || elems_per_scale % 4)) return set_error("saicv_dropout: elems_per_scale must be a positive multiple of 4");
   if (n % 4) return set_error("saicv_dropout: n %% 4 != 0");
   if (!(p >= 0.f && p < 1.f)) return set_error("saicv_dropout: p must be in [0, 1)");
   if (resid && !out_f32) return set_error("saicv_dropout: a residual needs an fp32 output");
-  const uint32_t thresh = dropout_threshold(p), lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
+  const uint32_t thresh = dropout_threshold(p);
   const float inv_keep = 1.f / (1.f - p);
   const int grid = grid_1d(n / 4);
-  if (in_f32 && out_f32) dropout_kernel<true, true><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, lo, hi);
-  else if (in_f32) dropout_kernel<true, false><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, lo, hi);
-  else if (out_f32) dropout_kernel<false, true><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, lo, hi);
-  else dropout_kernel<false, false><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, lo, hi);
+  if (in_f32 && out_f32) dropout_kernel<true, true><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, seed, seed_base);
+  else if (in_f32) dropout_kernel<true, false><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, seed, seed_base);
+  else if (out_f32) dropout_kernel<false, true><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, seed, seed_base);
+  else dropout_kernel<false, false><<<grid, 256, 0, ST>>>(in, resid, row_scale, elems_per_scale, out, n / 4, thresh, inv_keep, seed, seed_base);
   return check_launch("dropout_kernel");
 }
 

@@ -60,7 +60,7 @@ class _MHA:
     def _proj(self, x, r0, r1):
         return ops.linear_fwd(x, self.w_bf16[r0:r1], bias=self.mod.in_proj_bias.detach()[r0:r1])
 
-    def forward(self, q_in, k_in, v_in, t, B, Lq, Lk, key_bias, p, seed):
+    def forward(self, q_in, k_in, v_in, t, B, Lq, Lk, key_bias, p, seed, sb=None):
         """q_in [B*Lq, C], k_in / v_in [B*Lk, C] bf16 operand copies (q_in is k_in for self-attention).
         Returns the attention output [B*Lq, C] bf16 (before out_proj)."""
         C, H, hd = self.C, self.H, self.hd
@@ -84,8 +84,8 @@ class _MHA:
         vv = v.view(B, Lk, H, hd).permute(0, 2, 1, 3)
         att = torch.empty(B * Lq, C, device=v.device, dtype=torch.bfloat16)
         ov = att.view(B, Lq, H, hd).permute(0, 2, 1, 3)
-        _, lse = ops.attn_fwd(qe, ke, vv, kscale, out=ov, dropout_p=p, dropout_seed=seed)
-        t.update(qe=qe, ke=ke, vv=vv, ov=ov, lse=lse, kscale=kscale, biased=key_bias is not None, p=p, seed=seed,
+        _, lse = ops.attn_fwd(qe, ke, vv, kscale, out=ov, dropout_p=p, dropout_seed=seed, dropout_seed_base=sb)
+        t.update(qe=qe, ke=ke, vv=vv, ov=ov, lse=lse, kscale=kscale, biased=key_bias is not None, p=p, seed=seed, sb=sb,
                  dims=(B, Lq, Lk))
         t['att'] = att
         return att
@@ -110,14 +110,14 @@ class _MHA:
         if t['biased']:
             dqe, dke = torch.empty_like(t['qe']), torch.empty_like(t['ke'])
             ops.attn_bwd(t['qe'], t['ke'], t['vv'], t['ov'], t['lse'], dov, t['kscale'], dqe, dke, dvv, dk_cols=hd,
-                         dropout_p=t['p'], dropout_seed=t['seed'])
+                         dropout_p=t['p'], dropout_seed=t['seed'], dropout_seed_base=t['sb'])
             ops.heads_unpack(dqe, dq_dst, dq0, hd, scale=hd ** -0.5)
             ops.heads_unpack(dke, dk_dst, dk0, hd)
         else:
             dqv = dq_dst.view(B, Lq, -1)[:, :, dq0:dq0 + C].unflatten(2, (H, hd)).permute(0, 2, 1, 3)
             dkv = dk_dst.view(B, Lk, -1)[:, :, dk0:dk0 + C].unflatten(2, (H, hd)).permute(0, 2, 1, 3)
             ops.attn_bwd(t['qe'], t['ke'], t['vv'], t['ov'], t['lse'], dov, t['kscale'], dqv, dkv, dvv,
-                         dropout_p=t['p'], dropout_seed=t['seed'])
+                         dropout_p=t['p'], dropout_seed=t['seed'], dropout_seed_base=t['sb'])
         w, b = self.mod.in_proj_weight, self.mod.in_proj_bias
         wbuf, wacc = sink.begin(w)
         bbuf, bacc = sink.begin(b)
@@ -135,16 +135,16 @@ class _MHA:
         return ops.linear_dgrad(dy, self.w_bf16[r0:r1], resid=resid, out_f32=True)
 
 
-def _branch_out(lin, a, resid, p, seed):
+def _branch_out(lin, a, resid, p, seed, sb):
     """z = resid + dropout(lin(a)): the residual rides in the GEMM epilogue when there is no dropout."""
     if p == 0.:
         return lin.fwd(a, resid=resid, out_f32=True)
-    return ops.dropout(lin.fwd(a), p, seed, resid=resid)
+    return ops.dropout(lin.fwd(a), p, seed, resid=resid, seed_base=sb)
 
 
-def _branch_grad(dz, dzb, p, seed):
+def _branch_grad(dz, dzb, p, seed, sb):
     """bf16 gradient of the branch output from the gradient of z = resid + dropout(branch)."""
-    return dzb if p == 0. else ops.dropout(dz, p, seed, out_f32=False)
+    return dzb if p == 0. else ops.dropout(dz, p, seed, out_f32=False, seed_base=sb)
 
 
 class _FFN:
@@ -155,20 +155,20 @@ class _FFN:
         self.l1.prep()
         self.l2.prep()
 
-    def forward(self, yb, y, t, p, seeds):
+    def forward(self, yb, y, t, p, seeds, sb):
         """z = y + dropout(linear2(dropout(relu(linear1(yb)))))"""
         h = self.l1.fwd_flags(yb, ops.EPI_RELU)
         if p > 0.:
-            ops.dropout(h, p, seeds[0], out=h)
+            ops.dropout(h, p, seeds[0], out=h, seed_base=sb)
         t['ffn_in'], t['h'] = yb, h
-        return _branch_out(self.l2, h, y, p, seeds[1])
+        return _branch_out(self.l2, h, y, p, seeds[1], sb)
 
-    def backward(self, dz, dzb, t, sink, p, seeds):
+    def backward(self, dz, dzb, t, sink, p, seeds, sb):
         """Returns the fp32 gradient of y: dz (residual path) + the feed-forward path."""
-        g = _branch_grad(dz, dzb, p, seeds[1])
+        g = _branch_grad(dz, dzb, p, seeds[1], sb)
         dh = self.l2.bwd(g, t['h'], sink, relu_out=t['h'])          # zero where relu(.) = 0 or the unit was dropped
         if p > 0.:
-            ops.dropout(dh, p, seeds[0], out=dh)                   # survivors' 1 / (1 - p)
+            ops.dropout(dh, p, seeds[0], out=dh, seed_base=sb)     # survivors' 1 / (1 - p)
         self.l1.bwd(dh, t['ffn_in'], sink, need_dx=False)
         return ops.linear_dgrad(dh, self.l1.w_bf16, resid=dz, out_f32=True)
 
@@ -200,22 +200,22 @@ class _EncLayer:
 
     def forward(self, x, xb, xpb, t, cx, want_pos_copy):
         """x fp32 stream, xb = bf16(x), xpb = bf16(x + pos).  Returns the same triple for the next layer."""
-        p, s = cx['p'], cx['seed']()
+        p, s, sb = cx['p'], cx['seed'](), cx['sb']
         t['seeds'] = s
-        att = self.attn.forward(xpb, xpb, xb, t.setdefault('mha', {}), cx['B'], cx['L'], cx['L'], cx['key_bias'], p, s[0])
-        t['z1'] = z1 = _branch_out(self.attn.out, att, x, p, s[1])
+        att = self.attn.forward(xpb, xpb, xb, t.setdefault('mha', {}), cx['B'], cx['L'], cx['L'], cx['key_bias'], p, s[0], sb)
+        t['z1'] = z1 = _branch_out(self.attn.out, att, x, p, s[1], sb)
         y1, y1b, _, t['st1'] = _norm_fwd(self.layer.norm1, z1)
-        t['z2'] = z2 = self.ffn.forward(y1b, y1, t, p, s[2:4])
+        t['z2'] = z2 = self.ffn.forward(y1b, y1, t, p, s[2:4], sb)
         y2, y2b, y2pb, t['st2'] = _norm_fwd(self.layer.norm2, z2, pos=cx['pos'], want_ypb=want_pos_copy)
         return y2, y2b, y2pb
 
     def backward(self, dy2, t, sink, cx):
         """dy2 fp32: gradient of the layer output.  Returns the fp32 gradient of the layer input."""
-        p, s, C = cx['p'], t['seeds'], self.attn.C
+        p, s, C, sb = cx['p'], t['seeds'], self.attn.C, cx['sb']
         dz2, dz2b = _norm_bwd(self.layer.norm2, dy2, t['z2'], t['st2'], sink, want_dzb=(p == 0.))
-        dy1 = self.ffn.backward(dz2, dz2b, t, sink, p, s[2:4])
+        dy1 = self.ffn.backward(dz2, dz2b, t, sink, p, s[2:4], sb)
         dz1, dz1b = _norm_bwd(self.layer.norm1, dy1, t['z1'], t['st1'], sink, want_dzb=(p == 0.))
-        datt = self.attn.out.bwd(_branch_grad(dz1, dz1b, p, s[1]), t['mha']['att'], sink)
+        datt = self.attn.out.bwd(_branch_grad(dz1, dz1b, p, s[1], sb), t['mha']['att'], sink)
         dqk, _, dv = self.attn.backward(datt, t['mha'], sink)
         dx = self.attn.dgrad(dv, 2 * C, 3 * C, resid=dz1)
         return self.attn.dgrad(dqk, 0, 2 * C, resid=dx)
@@ -236,16 +236,16 @@ class _DecLayer:
     def forward(self, x, xb, xqb, memb, mempb, t, cx):
         """x fp32 [B*Q, C] (tgt), xb = bf16(x), xqb = bf16(x + query_pos); memb / mempb: bf16 copies of the encoder
         memory and memory + pos.  Returns (y3, y3b, y3qb)."""
-        p, s = cx['p'], cx['seed']()
+        p, s, sb = cx['p'], cx['seed'](), cx['sb']
         t['seeds'] = s
         B, Q, L = cx['B'], cx['Q'], cx['L']
-        att = self.sa.forward(xqb, xqb, xb, t.setdefault('sa', {}), B, Q, Q, None, p, s[0])
-        t['z1'] = z1 = _branch_out(self.sa.out, att, x, p, s[1])
+        att = self.sa.forward(xqb, xqb, xb, t.setdefault('sa', {}), B, Q, Q, None, p, s[0], sb)
+        t['z1'] = z1 = _branch_out(self.sa.out, att, x, p, s[1], sb)
         y1, _, y1qb, t['st1'] = _norm_fwd(self.layer.norm1, z1, pos=cx['qpos'], want_yb=False, want_ypb=True)
-        att = self.ca.forward(y1qb, mempb, memb, t.setdefault('ca', {}), B, Q, L, cx['key_bias'], p, s[2])
-        t['z2'] = z2 = _branch_out(self.ca.out, att, y1, p, s[3])
+        att = self.ca.forward(y1qb, mempb, memb, t.setdefault('ca', {}), B, Q, L, cx['key_bias'], p, s[2], sb)
+        t['z2'] = z2 = _branch_out(self.ca.out, att, y1, p, s[3], sb)
         y2, y2b, _, t['st2'] = _norm_fwd(self.layer.norm2, z2)
-        t['z3'] = z3 = self.ffn.forward(y2b, y2, t, p, s[4:6])
+        t['z3'] = z3 = self.ffn.forward(y2b, y2, t, p, s[4:6], sb)
         y3, y3b, y3qb, t['st3'] = _norm_fwd(self.layer.norm3, z3, pos=cx['qpos'], want_ypb=True)
         return y3, y3b, y3qb
 
@@ -253,11 +253,11 @@ class _DecLayer:
         """dy3 fp32: gradient of the layer output.  dmem / dqpos: running fp32 sums of the gradients of the encoder
         memory [B*L, C] and of the broadcast query positions [B*Q, C] (None before the first contribution).  Returns
         (dx fp32 | None, dmem, dqpos)."""
-        p, s, C = cx['p'], t['seeds'], self.sa.C
+        p, s, C, sb = cx['p'], t['seeds'], self.sa.C, cx['sb']
         dz3, dz3b = _norm_bwd(self.layer.norm3, dy3, t['z3'], t['st3'], sink, want_dzb=(p == 0.))
-        dy2 = self.ffn.backward(dz3, dz3b, t, sink, p, s[4:6])
+        dy2 = self.ffn.backward(dz3, dz3b, t, sink, p, s[4:6], sb)
         dz2, dz2b = _norm_bwd(self.layer.norm2, dy2, t['z2'], t['st2'], sink, want_dzb=(p == 0.))
-        datt = self.ca.out.bwd(_branch_grad(dz2, dz2b, p, s[3]), t['ca']['att'], sink)
+        datt = self.ca.out.bwd(_branch_grad(dz2, dz2b, p, s[3], sb), t['ca']['att'], sink)
         dq, dk, dv = self.ca.backward(datt, t['ca'], sink)
         dmem = self.ca.dgrad(dk, C, 2 * C, resid=dmem)               # keys see memory + pos, values memory
         dmem = self.ca.dgrad(dv, 2 * C, 3 * C, resid=dmem)
@@ -265,7 +265,7 @@ class _DecLayer:
         dqpos_new = gq                                               #   its gradient joins the query-pos sum ...
         dy1 = self.ca.dgrad(dq, 0, C, resid=dz2)                     #   ... and, with the residual path, y1
         dz1, dz1b = _norm_bwd(self.layer.norm1, dy1, t['z1'], t['st1'], sink, want_dzb=(p == 0.))
-        datt = self.sa.out.bwd(_branch_grad(dz1, dz1b, p, s[1]), t['sa']['att'], sink)
+        datt = self.sa.out.bwd(_branch_grad(dz1, dz1b, p, s[1], sb), t['sa']['att'], sink)
         dqk, _, dv = self.sa.backward(datt, t['sa'], sink)
         dqpos_new = self.sa.dgrad(dqk, 0, 2 * C, resid=dqpos_new)    # q = k = x + query_pos
         dx = None
@@ -332,17 +332,18 @@ class DetrRT:
     def _context(self, B, L, pos, key_bias, training):
         tr = self.model.transformer
         p = float(tr.dropout_prob) if training else 0.
-        base = 0
-        if p > 0.:   # one host-side draw per forward (torch's CPU generator: reproducible under torch.manual_seed)
-            base = int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 62) - 1)
+        # One random 62-bit word per forward, drawn ON THE DEVICE (torch's CUDA generator: reproducible under
+        # torch.manual_seed and graph-safe - a captured step draws a new word on every replay); the kernels add the
+        # per-site constants below to it (saicv_dropout's seed_base).
+        sb = torch.empty(1, dtype=torch.int64, device=pos.device).random_(0, 1 << 62) if p > 0. else None
         counter = [0]
 
         def seeds():
             counter[0] += 8
-            return [base + counter[0] + i for i in range(8)]
+            return [counter[0] + i for i in range(8)]
 
         return {'B': B, 'L': L, 'Q': self.model.query_embed.weight.shape[0], 'pos': pos, 'key_bias': key_bias, 'p': p,
-                'seed': seeds, 'qpos': self.model.query_embed.weight.detach()}
+                'seed': seeds, 'sb': sb, 'qpos': self.model.query_embed.weight.detach()}
 
     # ---- stages (tests drive them separately with the oracle's tensors)
     def backbone_forward(self, x, tape, training, keep_tape):

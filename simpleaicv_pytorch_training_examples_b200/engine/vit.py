@@ -94,25 +94,25 @@ class _Block:
             s.div_(keep)
         return s
 
-    def forward(self, x, t, b, l, training, p=0., seeds=None, scales=None):
+    def forward(self, x, t, b, l, training, p=0., seeds=None, scales=None, sb=None):
         """x: fp32 [B*L, C] -> fp32 [B*L, C].  p: dropout probability of this pass (vit.py:59,73-78,90-97: attention
         probabilities, after proj, after GELU, after fc2) with the counter-hash seeds `seeds`; scales: drop-path
         scales to reuse (the recomputation of a checkpointed block must see the forward's draws)."""
         blk, c = self.blk, x.shape[1]
         d = c // self.heads
-        t['x_in'], t['p'], t['seeds'] = x, p, seeds
+        t['x_in'], t['p'], t['seeds'], t['sb'] = x, p, seeds, sb
         t['ln1'], t['st1'] = ops.layernorm_fwd(x, blk.norm1.weight.detach(), blk.norm1.bias.detach(), blk.norm1.eps)
         t['qkv'] = self.qkv.fwd(t['ln1'])
         if p > 0.:
             q, k, v = (t['qkv'].view(b, l, 3, self.heads, d)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
             t['att'] = torch.empty(b * l, c, device=x.device, dtype=torch.bfloat16)
             _, t['lse'] = ops.attn_fwd(q, k, v, self.scale, out=t['att'].view(b, l, self.heads, d).permute(0, 2, 1, 3),
-                                       dropout_p=p, dropout_seed=seeds[0])
+                                       dropout_p=p, dropout_seed=seeds[0], dropout_seed_base=sb)
         else:
             t['att'], t['lse'] = ops.attention_fwd(t['qkv'], b, l, self.heads, d, self.scale)
         s1 = t['s1'] = scales[0] if scales is not None else self._path_scale(b, l, training, x.device)
         if p > 0.:
-            x = ops.dropout(self.proj.fwd(t['att']), p, seeds[1], resid=x, row_scale=s1, elems_per_scale=l * c)
+            x = ops.dropout(self.proj.fwd(t['att']), p, seeds[1], resid=x, row_scale=s1, elems_per_scale=l * c, seed_base=sb)
         else:
             x = self.proj.fwd(t['att'], resid=x, out_f32=True, row_scale=s1, rows_per_scale=l)
         t['x_mid'] = x
@@ -120,10 +120,10 @@ class _Block:
         t['u'] = self.fc1.fwd(t['ln2'])
         t['h'] = ops.gelu_fwd(t['u'])
         if p > 0.:
-            ops.dropout(t['h'], p, seeds[2], out=t['h'])
+            ops.dropout(t['h'], p, seeds[2], out=t['h'], seed_base=sb)
         s2 = t['s2'] = scales[1] if scales is not None else self._path_scale(b, l, training, x.device)
         if p > 0.:
-            return ops.dropout(self.fc2.fwd(t['h']), p, seeds[3], resid=x, row_scale=s2, elems_per_scale=l * c)
+            return ops.dropout(self.fc2.fwd(t['h']), p, seeds[3], resid=x, row_scale=s2, elems_per_scale=l * c, seed_base=sb)
         return self.fc2.fwd(t['h'], resid=x, out_f32=True, row_scale=s2, rows_per_scale=l)
 
     def _ln_bwd(self, norm, dy, x, stats, dres, sink, scale, l):
@@ -143,16 +143,16 @@ class _Block:
         `next_scale`, the MLP drop-path scale of the block that consumes it)."""
         blk = self.blk
         d = dx.shape[1] // self.heads
-        p, seeds = t['p'], t['seeds']
+        p, seeds, sb = t['p'], t['seeds'], t['sb']
         # ---- MLP branch: fc2 data gradient comes out already multiplied by gelu'(u)
-        g = ops.dropout(dxb, p, seeds[3]) if p > 0. else dxb
+        g = ops.dropout(dxb, p, seeds[3], seed_base=sb) if p > 0. else dxb
         du = self.fc2.bwd(g, t['h'], sink, gelu_pre=t['u'])
         if p > 0.:
-            ops.dropout(du, p, seeds[2], out=du)
+            ops.dropout(du, p, seeds[2], out=du, seed_base=sb)
         dln2 = self.fc1.bwd(du, t['ln2'], sink)
         dx, dxb = self._ln_bwd(blk.norm2, dln2, t['x_mid'], t['st2'], dx, sink, t['s1'], l)
         # ---- attention branch
-        g = ops.dropout(dxb, p, seeds[1]) if p > 0. else dxb
+        g = ops.dropout(dxb, p, seeds[1], seed_base=sb) if p > 0. else dxb
         datt = self.proj.bwd(g, t['att'], sink)
         if p > 0.:
             c = dx.shape[1]
@@ -160,7 +160,7 @@ class _Block:
             dqkv = torch.empty_like(t['qkv'])
             dq, dk, dv = (dqkv.view(b, l, 3, self.heads, d)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
             ops.attn_bwd(qv, kv, vv, t['att'].view(b, l, self.heads, d).permute(0, 2, 1, 3), t['lse'],
-                         datt.view(b, l, self.heads, d).permute(0, 2, 1, 3), self.scale, dq, dk, dv, dropout_p=p, dropout_seed=seeds[0])
+                         datt.view(b, l, self.heads, d).permute(0, 2, 1, 3), self.scale, dq, dk, dv, dropout_p=p, dropout_seed=seeds[0], dropout_seed_base=sb)
         else:
             dqkv = ops.attention_bwd(t['qkv'], t['att'], datt, t['lse'], b, l, self.heads, d, self.scale)
         dln1 = self.qkv.bwd(dqkv, t['ln1'], sink)
@@ -223,23 +223,23 @@ class ViTRT:
         m = self.model
         tape = {'blocks': [dict() for _ in self.blocks]}
         p = float(getattr(m, 'dropout_prob', 0.)) if training else 0.
-        base = 0
-        if p > 0.:   # one host-side draw per forward (torch's CPU generator: reproducible under torch.manual_seed)
-            base = int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 62) - 1)
-        tape['p'], tape['embed_seed'] = p, base
+        # one random 62-bit word per forward drawn on the device (torch's CUDA generator: reproducible under
+        # torch.manual_seed, and graph-safe: a captured step draws a new word every replay); per-site constants are added
+        sb = torch.empty(1, dtype=torch.int64, device=x.device).random_(0, 1 << 62) if p > 0. else None
+        tape['p'], tape['sb'] = p, sb
         h = self.embed_forward(x.contiguous(), tape)
         if p > 0.:   # vit.py:244 embedding_dropout
-            ops.dropout(h, p, base, out=h)
+            ops.dropout(h, p, 0, out=h, seed_base=sb)
         ckpt = keep_tape and getattr(m, 'use_gradient_checkpoint', False)
         for i, (blk, t) in enumerate(zip(self.blocks, tape['blocks'])):
-            seeds = [base + 8 * (i + 1) + j for j in range(4)]
+            seeds = [8 * (i + 1) + j for j in range(4)]
             if ckpt:   # vit.py:247-249: keep the block input (and this pass's random draws), recompute in backward
                 scratch = {}
-                out = blk.forward(h, scratch, tape['b'], tape['l'], training, p, seeds)
-                t.update(ckpt_in=h, ckpt_scales=(scratch['s1'], scratch['s2']), s2=scratch['s2'], p=p, seeds=seeds)
+                out = blk.forward(h, scratch, tape['b'], tape['l'], training, p, seeds, sb=sb)
+                t.update(ckpt_in=h, ckpt_scales=(scratch['s1'], scratch['s2']), s2=scratch['s2'], p=p, seeds=seeds, sb=sb)
                 h = out
             else:
-                h = blk.forward(h, t, tape['b'], tape['l'], training, p, seeds)
+                h = blk.forward(h, t, tape['b'], tape['l'], training, p, seeds, sb=sb)
         logits = self.head_forward(h, tape)
         return logits, (tape if keep_tape else None)
 
@@ -307,11 +307,11 @@ class ViTRT:
             nxt = tapes[i - 1]['s2'] if i > 0 else None
             t = tapes[i]
             if 'ckpt_in' in t:
-                self.blocks[i].forward(t.pop('ckpt_in'), t, tape['b'], tape['l'], True, t['p'], t['seeds'], scales=t.pop('ckpt_scales'))
+                self.blocks[i].forward(t.pop('ckpt_in'), t, tape['b'], tape['l'], True, t['p'], t['seeds'], scales=t.pop('ckpt_scales'), sb=t['sb'])
             dx, dxb = self.blocks[i].backward(dx, dxb, t, tape['b'], tape['l'], sink, next_scale=nxt)
             t.clear()
         if tape['p'] > 0.:
-            ops.dropout(dx, tape['p'], tape['embed_seed'], out=dx)
+            ops.dropout(dx, tape['p'], 0, out=dx, seed_base=tape['sb'])
         self.embed_backward(dx, tape)
         if sink.on_backward_end is not None:
             sink.on_backward_end()

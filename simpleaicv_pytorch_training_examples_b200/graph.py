@@ -11,8 +11,10 @@ Constraints (checked / documented): fixed batch shape; the optimizer's hyper-par
 unless they are device tensors (use a tensor ``lr`` for per-iteration schedules; AdamW needs ``capturable=True``).
 Under data parallelism the model may be the ``B200DataParallel`` wrapper: its bucket all-reduces (NCCL, issued on the
 side stream from the backward's gradient-ready callbacks with event fork / join against the compute stream) are captured
-into the same graph (measured at N = 2: 28.7 -> 27.4 ms per ResNet-50 step, end to end 34.6 -> 27.9 ms).  Dropout seeds
-drawn on the host are constants of the captured step: train with dropout eagerly.
+into the same graph (measured at N = 2: 28.7 -> 27.4 ms per ResNet-50 step, end to end 34.6 -> 27.9 ms).  Dropout is
+graph-safe: the runtimes draw one random word per forward on the device (captured: a new word every replay) and the
+dropout / attention kernels add their per-site constants to it (saicv_dropout's seed_base), so the masks change from
+step to step although the launch arguments are constants of the graph.
 """
 import torch
 

@@ -411,7 +411,7 @@ def pack_key_mask(mask, lk):
     return w.to(torch.int32).contiguous()
 
 
-def _attn_args(q, k, v, out, lse, scale, mask_bits, dropout_p=0.0, dropout_seed=0):
+def _attn_args(q, k, v, out, lse, scale, mask_bits, dropout_p=0.0, dropout_seed=0, dropout_seed_base=None):
     a = _lib.AttnArgs()
     b, h, lq, dqk = q.shape
     lk, dv = k.shape[2], v.shape[3]
@@ -422,10 +422,11 @@ def _attn_args(q, k, v, out, lse, scale, mask_bits, dropout_p=0.0, dropout_seed=
     a.mask_words = mask_bits.shape[1] if mask_bits is not None else 0
     a.b, a.h, a.lq, a.lk, a.dqk, a.dv, a.scale = b, h, lq, lk, dqk, dv, scale
     a.dropout_p, a.dropout_seed = float(dropout_p), int(dropout_seed)
+    a.dropout_seed_base = dropout_seed_base.data_ptr() if dropout_seed_base is not None else None
     return a
 
 
-def attn_fwd(q, k, v, scale, out=None, mask_bits=None, dropout_p=0.0, dropout_seed=0):
+def attn_fwd(q, k, v, scale, out=None, mask_bits=None, dropout_p=0.0, dropout_seed=0, dropout_seed_base=None):
     """General fused attention.  q [B, H, Lq, Dqk], k [B, H, Lk, Dqk], v [B, H, Lk, Dv]: bf16 VIEWS with a
     contiguous last dimension (any batch / head / row strides).  out: [B, H, Lq, Dv] view to write (default:
     a [B, Lq, H, Dv] buffer viewed as [B, H, Lq, Dv], i.e. heads concatenated per token).  dropout_p > 0: dropout on
@@ -436,17 +437,17 @@ def attn_fwd(q, k, v, scale, out=None, mask_bits=None, dropout_p=0.0, dropout_se
     if out is None:
         out = torch.empty(b, lq, h, dv, device=q.device, dtype=torch.bfloat16).permute(0, 2, 1, 3)
     lse = torch.empty(b, h, lq, device=q.device, dtype=torch.float32)
-    a = _attn_args(q, k, v, out, lse, scale, mask_bits, dropout_p, dropout_seed)
+    a = _attn_args(q, k, v, out, lse, scale, mask_bits, dropout_p, dropout_seed, dropout_seed_base)
     _lib.call('saicv_attn_fwd', ctypes.byref(a), _stream())
     return out, lse
 
 
-def attn_bwd(q, k, v, out, lse, dout, scale, dq, dk, dv, dk_cols=0, mask_bits=None, dropout_p=0.0, dropout_seed=0):
+def attn_bwd(q, k, v, out, lse, dout, scale, dq, dk, dv, dk_cols=0, mask_bits=None, dropout_p=0.0, dropout_seed=0, dropout_seed_base=None):
     """Gradients of attn_fwd written into the given [B, H, L, D] views dq (Dqk cols), dk (leading dk_cols
     columns; 0 = all) and dv."""
     assert dout.stride() == out.stride(), 'dout must have the layout of out'
     a = _lib.AttnBwdArgs()
-    a.fwd = _attn_args(q, k, v, out, lse, scale, mask_bits, dropout_p, dropout_seed)
+    a.fwd = _attn_args(q, k, v, out, lse, scale, mask_bits, dropout_p, dropout_seed, dropout_seed_base)
     delta = torch.empty_like(lse)
     a.dout, a.delta = dout.data_ptr(), delta.data_ptr()
     a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
@@ -656,15 +657,16 @@ def add_pos_cast(x, pos=None, want_xb=True, want_xpb=True):
     return xb, xpb
 
 
-def dropout(x, p, seed, resid=None, out_f32=None, out=None, row_scale=None, elems_per_scale=0):
+def dropout(x, p, seed, resid=None, out_f32=None, out=None, row_scale=None, elems_per_scale=0, seed_base=None):
     """out = (keep ? x / (1 - p) : 0) * row_scale[index // elems_per_scale] (+ resid); counter-hash mask
-    (csrc/dropout_hash.cuh), same seed => same mask."""
+    (csrc/dropout_hash.cuh), same seed => same mask.  seed_base: int64 device tensor [1] added to `seed` on the device
+    (graph-safe: a captured step refreshes it every replay)."""
     if out_f32 is None:
         out_f32 = x.dtype == torch.float32 or resid is not None
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
     _lib.call('saicv_dropout', _p(x), int(x.dtype == torch.float32), _p(resid), _p(row_scale), elems_per_scale, _p(out), int(out_f32),
-              x.numel(), float(p), int(seed), _stream())
+              x.numel(), float(p), int(seed), _p(seed_base), _stream())
     return out
 
 

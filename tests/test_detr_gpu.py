@@ -53,6 +53,8 @@ def test_dropout_kernel_matches_hash_and_backward_is_same_mask():
     got2 = ops.dropout(x.cuda(), p, seed, resid=r.cuda())
     assert got2.dtype == torch.float32
     torch.testing.assert_close(got2.cpu(), want + r, rtol=1e-6, atol=1e-6)
+    base = torch.tensor([123456789012345], dtype=torch.int64, device='cuda')   # device-resident part of the seed
+    assert torch.equal(ops.dropout(x.cuda(), p, seed - 123456789012345, seed_base=base), got)
     g = torch.randn(n)
     gb = ops.dropout(g.cuda(), p, seed, out_f32=False)          # backward of the residual-branch dropout
     assert _rel(gb, torch.where(keep, g / (1 - p), torch.zeros(())).bfloat16()) < 1e-4     # x * (1 / (1 - p)) vs x / (1 - p): 1 ulp before the bf16 rounding
@@ -143,6 +145,10 @@ def test_attention_bias_column_and_probability_dropout(B, H, Lq, Lk, dqk, p):
     qc, kc, vc = q.cuda(), k.cuda(), v.cuda()
     out, lse = ops.attn_fwd(qc, kc, vc, scale, dropout_p=p, dropout_seed=seed)
     assert _rel(out, want.detach()) < 1.5e-2, _rel(out, want.detach())
+    if p > 0:   # the same seed split into a launch constant and a device-resident base gives the same masks
+        base = torch.tensor([seed - 77], dtype=torch.int64, device='cuda')
+        out2, _ = ops.attn_fwd(qc, kc, vc, scale, dropout_p=p, dropout_seed=77, dropout_seed_base=base)
+        assert torch.equal(out2, out)
     dq, dk, dv = torch.zeros_like(qc), torch.zeros_like(kc), torch.empty_like(vc)
     doc = do.cuda().permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)      # the layout of `out` ([B, L, H, D] storage)
     ops.attn_bwd(qc, kc, vc, out, lse, doc, scale, dq, dk, dv, dk_cols=hd if dqk == 48 else 0, dropout_p=p, dropout_seed=seed)

@@ -175,3 +175,24 @@ def test_vit_dropout_paths():
     m.eval()
     with torch.no_grad():
         assert torch.equal(m(x), m(x))
+
+
+def test_vit_dropout_inside_a_cuda_graph_draws_new_masks_every_replay():
+    """graph.GraphedTrainStep with dropout_prob > 0: the random word of the step lives on the device and is re-drawn inside
+    the captured step, so consecutive replays on the SAME batch (and frozen weights: lr 0) give different losses, while an
+    identical second model replayed from the same generator state reproduces them exactly."""
+    from simpleaicv_pytorch_training_examples_b200.graph import GraphedTrainStep
+    g = torch.Generator().manual_seed(7)
+    x, y = torch.randn(4, 3, 64, 64, generator=g).cuda(), torch.randint(0, 10, (4,), generator=g).cuda()
+    crit = torch.nn.CrossEntropyLoss()
+
+    def run(seed):
+        m = _small_vit(dropout_prob=0.2)
+        opt = torch.optim.SGD(m.parameters(), lr=0.0)
+        torch.manual_seed(seed)
+        step = GraphedTrainStep(m, lambda o, t: crit(o.float(), t), opt, x, y)
+        return [float(step(x, y)) for _ in range(3)]
+
+    a, b = run(11), run(11)
+    assert len(set(a)) == 3, a            # new masks on every replay
+    assert a == b                         # reproducible from the generator state
