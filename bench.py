@@ -429,7 +429,8 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
             return sum(detr_crit(outs, y).values())
 
         class _Cfg:
-            optimizer = ('AdamW', {'lr': 1e-4, 'global_weight_decay': False, 'weight_decay': 1e-4, 'no_weight_decay_layer_name_list': []})
+            optimizer = ('AdamW', {'lr': 1e-4, 'global_weight_decay': False, 'weight_decay': 1e-4, 'no_weight_decay_layer_name_list': [],
+                                   'capturable': True})
         opt, _ = tutils.build_optimizer(_Cfg, model)
     elif model_name == 'sam_h_encoder':
         from simpleaicv_pytorch_training_examples_b200.interactive_segmentation.models.segment_anything import sam
@@ -520,8 +521,22 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
             graphed, graph_note = None, f'eager (graph capture failed: {type(e).__name__}: {e})'
             torch.cuda.synchronize()
 
+    split = None
+    if detr_masks is not None and not args.no_graph and (world == 1 or not args.no_graph_ddp):
+        try:   # the criterion needs the host (Hungarian matcher): forward graph + eager criterion + backward/optimizer graph
+            from simpleaicv_pytorch_training_examples_b200.graph import GraphedSplitStep
+            torch.cuda.empty_cache()
+            split = GraphedSplitStep(lambda x: net(x), lambda outs, y: detr_crit(outs, y), opt, [x_dev], y_dev)
+            graph_note = 'two CUDA graphs per step around the eager criterion (graph.GraphedSplitStep)' + (', NCCL captured' if world > 1 else '')
+        except Exception as e:  # pragma: no cover
+            split, graph_note = None, f'eager (graph capture failed: {type(e).__name__}: {e})'
+            torch.cuda.synchronize()
+
     # device-resident throughput: the same graph replayed on resident inputs when there is one, else the eager loop above
-    if graphed is not None:
+    if split is not None:
+        split([x_dev], y_dev)
+        ms_step = timed(lambda: split([x_dev], y_dev), steps) / steps
+    elif graphed is not None:
         graphed.replay()
         ms_step = timed(graphed.replay, steps) / steps
     else:
@@ -530,8 +545,10 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
 
     def e2e_loop(k):
         host_batches = ({'image': x_host, 'label': y_host} for _ in range(k))
-        for batch in tutils.CudaPrefetcher(host_batches, dev):
-            if graphed is not None:
+        for batch in tutils.CudaPrefetcher(host_batches, dev, copy_streams=args.prefetch_streams):
+            if split is not None:
+                split([batch['image']], batch['label']).item()
+            elif graphed is not None:
                 graphed(batch['image'], batch['label']).item()
             else:
                 step(batch['image'], batch['label']).item()
@@ -650,6 +667,7 @@ def main():
     ap.add_argument('--sam', action='store_true', help='add the SAM ViT-H image-encoder sub-record (BASELINE configs[3]: bs8, 1024x1024)')
     ap.add_argument('--no-graph-ddp', action='store_true',
                     help='N > 1: launch the step eagerly instead of capturing it (NCCL bucket all-reduces included) in one CUDA graph')
+    ap.add_argument('--prefetch-streams', type=int, default=4, help='copy streams of the end-to-end host prefetcher (tools.utils.CudaPrefetcher)')
     ap.add_argument('--no-graph', action='store_true', help='end-to-end loop without the CUDA graph (eager launches)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))

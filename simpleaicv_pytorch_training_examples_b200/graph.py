@@ -58,3 +58,60 @@ class GraphedTrainStep:
         self.static_y.copy_(y, non_blocking=True)
         self.graph.replay()
         return self.static_loss
+
+
+class GraphedSplitStep:
+    """Two CUDA graphs around an eager criterion, for steps whose loss needs the host (DETR's Hungarian matcher,
+    detection/losses.py): graph A = model forward, then the criterion runs eagerly on the (detached) outputs and autograd
+    gives their gradients, graph B = the runtime's backward + optimizer step + zero_grad, replayed with those gradients in
+    static buffers.  Both graphs share one memory pool, so the activations A leaves on the runtime's tape are exactly what
+    B reads.  ``model_fn(*inputs)`` returns a tensor or a list / tuple of tensors; ``criterion(outputs, targets)`` a scalar
+    or a dict of loss terms (summed)."""
+
+    def __init__(self, model_fn, criterion, optimizer, example_inputs, example_targets, warmup=3):
+        dev = example_inputs[0].device
+        self.model_fn, self.criterion, self.optimizer = model_fn, criterion, optimizer
+        self.static_in = [t.clone() for t in example_inputs]
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):      # warm-up on a side stream (allocator / lazy-init work must not be captured)
+            for _ in range(warmup):
+                outs = self._as_list(model_fn(*self.static_in))
+                self._loss(outs, example_targets).backward()
+                optimizer.step()
+                optimizer.zero_grad()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fwd):
+            self.outs = self._as_list(model_fn(*self.static_in))
+        self.static_grads = [torch.zeros_like(o) for o in self.outs]
+        self.graph_bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_bwd, pool=self.graph_fwd.pool()):
+            torch.autograd.backward(self.outs, self.static_grads)
+            optimizer.step()
+            optimizer.zero_grad()
+
+    @staticmethod
+    def _as_list(o):
+        return [o] if torch.is_tensor(o) else list(o)
+
+    def _loss(self, outs, targets):
+        value = self.criterion(outs if len(outs) > 1 else outs[0], targets)
+        return sum(value.values()) if isinstance(value, dict) else value
+
+    def __call__(self, inputs, targets):
+        """One training step; returns the (eager) loss tensor."""
+        for s, t in zip(self.static_in, inputs):
+            s.copy_(t, non_blocking=True)
+        self.graph_fwd.replay()
+        leaves = [o.detach().requires_grad_(True) for o in self.outs]
+        loss = self._loss(leaves, targets)
+        grads = torch.autograd.grad(loss, leaves, allow_unused=True)
+        for s, g in zip(self.static_grads, grads):
+            if g is None:
+                s.zero_()
+            else:
+                s.copy_(g)
+        self.graph_bwd.replay()
+        return loss.detach()

@@ -267,3 +267,40 @@ def test_detr_eval_determinism_and_dropout_training():
     assert torch.isfinite(outs[2][1]).all()
     with pytest.raises(RuntimeError):
         model(x, masks)                                           # CPU tensors: there is no fallback path
+
+
+def test_detr_split_graph_step_matches_eager_steps():
+    """graph.GraphedSplitStep (forward graph + eager DETRLoss with the host-side Hungarian matcher + backward / optimizer
+    graph) reproduces eager training steps bit for bit (dropout 0: same kernels, same order, same inputs)."""
+    from simpleaicv_pytorch_training_examples_b200.detection import models
+    from simpleaicv_pytorch_training_examples_b200.detection.losses import DETRLoss
+    from simpleaicv_pytorch_training_examples_b200.graph import GraphedSplitStep
+    shape = (2, 3, 128, 160)
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(*shape, generator=g).cuda() for _ in range(3)]
+    masks = make_golden.detr_masks(shape).cuda()
+    ann = torch.cat([torch.rand(2, 4, 2, generator=g) * 0.6 + 0.2, torch.rand(2, 4, 2, generator=g) * 0.3 + 0.05,
+                     torch.randint(0, 80, (2, 4, 1), generator=g).float()], dim=2).cuda()
+    crit = DETRLoss().cuda()
+
+    def build():
+        torch.manual_seed(3)
+        m = models.resnet18_detr().cuda().train()
+        m.transformer.dropout_prob = 0.0
+        return m, torch.optim.AdamW(m.parameters(), lr=1e-4, capturable=True)
+
+    m1, o1 = build()
+    eager = []
+    for i in range(6):                       # 3 warm-up steps (the graphed step warms up on its example batch) + 3 compared
+        out = m1(xs[0] if i < 3 else xs[i - 3], masks)
+        loss = sum(crit(out, ann).values())
+        loss.backward()
+        o1.step()
+        o1.zero_grad()
+        eager.append(float(loss))
+    m2, o2 = build()
+    step = GraphedSplitStep(lambda x: m2(x, masks), crit, o2, [xs[0]], ann)
+    graphed = [float(step([x], ann)) for x in xs]
+    assert graphed == eager[3:], (graphed, eager[3:])
+    for (n, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(p, q), n
