@@ -366,6 +366,43 @@ int saicv_sam_loss_sums(const void* logits, int logits_bf16, const float* target
 int saicv_sam_loss_bwd(const void* logits, int logits_bf16, const float* targets, const float* coef, void* dlogits,
                        int dl_bf16, int b, int m, long long n, float alpha, float gamma, void* stream);
 
+/* ---- multi-tensor optimizer step (csrc/capi_optim.cu) --------------------------------------------------
+ * Replaces torch.optim.SGD / torch.optim.AdamW as the reference builds them (tools/utils.py:292-600, stepped at
+ * tools/scripts.py:209-248) with ONE launch over all parameters, the refresh of the bf16 GEMM-operand copies and the
+ * global-norm gradient clip (torch.nn.utils.clip_grad_norm_, tools/scripts.py:226-236) fused in.
+ * tensors: device array of saicv_opt_tensor; chunk_tensor / chunk_index: device int arrays, block b updates elements
+ * [chunk_index[b] * SAICV_OPT_CHUNK, +SAICV_OPT_CHUNK) of tensor chunk_tensor[b].
+ * hyper: device fp32 [SAICV_OPT_RING][n_groups][8]; the update reads table (*step %% SAICV_OPT_RING) and a one-thread
+ * kernel then advances *step (device int).  Rows:
+ *   SGD   {lr, weight_decay, momentum, nesterov, 0...}       (dampening 0; buf = momentum buf + (g + wd p); p -= lr buf)
+ *   AdamW {lr, weight_decay, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t), 0}   (torch.optim.AdamW's update)
+ * clip: device fp32 [2] = {gradient scale, global norm} written by saicv_multi_tensor_clip_coef, or NULL.  All launch
+ * arguments are step-invariant: a captured step replays with new learning rates once the host has rewritten slot
+ * t %% SAICV_OPT_RING of the (pinned) table the captured copy brings in. */
+#define SAICV_OPT_CHUNK 8192
+#define SAICV_OPT_RING 8
+typedef struct {
+  float* p;            /* fp32 master parameter */
+  const float* g;      /* fp32 gradient */
+  float* s1;           /* SGD momentum buffer / AdamW exp_avg */
+  float* s2;           /* AdamW exp_avg_sq (NULL for SGD) */
+  void* shadow;        /* bf16 operand copy refreshed in the same pass, or NULL */
+  long long numel;
+  int group;           /* row of `hyper` */
+  int rs;              /* shadow layout: 0 = same linear index ([N][K] Linear weights); > 0 = conv weight [K][C][rs taps]
+                          -> [K][kpad] with column tap * cp + c (saicv_prep_conv_weight order 0) */
+  int c, cp, kpad;
+  int pad_;
+} saicv_opt_tensor;
+int saicv_opt_chunk(void);
+int saicv_multi_tensor_sgd(const void* tensors, const int* chunk_tensor, const int* chunk_index, int n_chunks,
+                           const float* hyper, int n_groups, int* step, const float* clip, void* stream);
+int saicv_multi_tensor_adamw(const void* tensors, const int* chunk_tensor, const int* chunk_index, int n_chunks,
+                             const float* hyper, int n_groups, int* step, const float* clip, void* stream);
+/* partial: fp32 [n_chunks] workspace; clip = {min(1, max_norm / (norm + 1e-6)), norm}; fixed summation order. */
+int saicv_multi_tensor_clip_coef(const void* tensors, const int* chunk_tensor, const int* chunk_index, int n_chunks,
+                                 float max_norm, float* partial, float* clip, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -120,8 +121,44 @@ bool encode_im2col(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, 
   return true;
 }
 
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Debug / tuning override read at every launch: SAICV_GEMM_TUNE="bn:stages:store_bufs" (0 = keep the default).
+void tune_override(int* bn, int* stages, int* nb) {
+  const char* e = getenv("SAICV_GEMM_TUNE");
+  if (!e || !*e) return;
+  int a = 0, b = 0, c = 0;
+  sscanf(e, "%d:%d:%d", &a, &b, &c);
+  if (bn && (a == 64 || a == 128 || a == 192 || a == 256)) *bn = a;
+  if (stages && b > 0) *stages = b;
+  if (nb && c > 0) *nb = c;
+}
+
+// Split of the 227 KB between the operand ring (stages) and the epilogue staging slices (nb per half).
+// A tile whose reduction is >= 4 k-blocks long keeps the tensor pipe busy for > 1 us, which hides a
+// serialised epilogue: it gets >= 4 ring stages and whatever is left for the slices.  Short reductions
+// (the 1x1 convolutions of layers 1-3, K = 64..256) are epilogue / HBM bound: 3 stages are enough
+// to keep the loads of the following tiles in flight and the rest goes to 2-3 slices per half.
 template <int BN>
-int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const GemmParams& p,
+void pick_smem_split(const GemmParams& p, int stat_bytes, int* stages_out, int* nb_out) {
+  using Cfg = GemmCfg<BN>;
+  const int budget = kSmemBudget - stat_bytes;
+  const bool has_aux = p.aux_tma != 0;
+  const int min_stages = p.kb_per_split >= 4 ? 4 : 3;
+  int nb = has_aux ? 3 : 2;
+  while (nb > 1 && (budget - 2 * nb * kStoreBufBytes) / Cfg::kStageBytes < min_stages) --nb;
+  int stages = (budget - 2 * nb * kStoreBufBytes) / Cfg::kStageBytes;
+  tune_override(nullptr, &stages, &nb);
+  if (nb > kMaxStoreBufs) nb = kMaxStoreBufs;
+  const int fit = (budget - 2 * nb * kStoreBufBytes) / Cfg::kStageBytes;
+  if (stages > fit) stages = fit;
+  if (stages > Cfg::kStages) stages = Cfg::kStages;
+  *stages_out = stages;
+  *nb_out = nb;
+}
+
+template <int BN>
+int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& r, const GemmParams& p,
            cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
@@ -134,13 +171,13 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, con
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
   const long long total = (long long)num_m * num_n * p.splits;
   const int grid = (int)(total < g_sm_count ? total : g_sm_count);
-  // smem ring depth: everything that fits next to the store buffers (and the stats accumulators)
   const int stat_bytes = (p.epi_flags & EPI_STATS) ? ((8 * p.N + 15) & ~15) : 0;
-  int stages = (kSmemBudget - 2 * kStoreBufBytes - stat_bytes) / Cfg::kStageBytes;
-  if (stages > Cfg::kStages) stages = Cfg::kStages;
+  int stages = 0, nb = 1;
+  pick_smem_split<BN>(p, stat_bytes, &stages, &nb);
   if (stages < 2) return set_error("gemm_sm100_kernel<%d>: %d bytes of statistics do not fit in shared memory", BN, stat_bytes);
   const_cast<GemmParams&>(p).num_stages = stages;
-  gemm_sm100_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a, b, d, p);
+  const_cast<GemmParams&>(p).store_bufs = nb;
+  gemm_sm100_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a, b, d, r, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm_sm100_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
   count_launch(1);
@@ -156,21 +193,30 @@ int pick_bn(int N) {
     const long long cost = (long long)((N + cand[i] - 1) / cand[i]) * cand[i];
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cand[i]; }
   }
+  tune_override(&best, nullptr, nullptr);
   return best;
 }
 
+// `aux` / `aux_f32`: the epilogue operand of the output's shape (fp32 residual or bf16 addend / mask /
+// pre-activation).  When its element width equals the output's it travels by TMA (GemmParams::aux_tma).
 int dispatch(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, GemmParams& p,
-             cudaStream_t st) {
+             cudaStream_t st, const void* aux = nullptr, bool aux_f32 = false) {
   p.idesc = make_idesc_bf16(128, bn, p.a_mode == A_MN2D ? 1 : 0, p.b_mode != B_K2D ? 1 : 0);
+  CUtensorMap r = d;
+  p.aux_tma = 0;
+  const bool both = (p.epi_flags & EPI_RESID) && (p.epi_flags & (EPI_RESID_BF16 | EPI_MUL_DGELU | EPI_MUL_DRELU));
+  if (aux && !both && !(p.epi_flags & EPI_DIRECT) && p.splits == 1 && aux_f32 == (p.out_f32 != 0) && aligned16(aux) &&
+      !getenv("SAICV_GEMM_NO_AUX_TMA")) {
+    if (!encode_out(&r, aux, aux_f32, p.N, p.M, p.ldd, 1, 0)) return 2;
+    p.aux_tma = 1;
+  }
   switch (bn) {
-    case 64: return launch<64>(a, b, d, p, st);
-    case 128: return launch<128>(a, b, d, p, st);
-    case 192: return launch<192>(a, b, d, p, st);
-    default: return launch<256>(a, b, d, p, st);
+    case 64: return launch<64>(a, b, d, r, p, st);
+    case 128: return launch<128>(a, b, d, r, p, st);
+    case 192: return launch<192>(a, b, d, r, p, st);
+    default: return launch<256>(a, b, d, r, p, st);
   }
 }
-
-bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
 
@@ -227,7 +273,7 @@ int saicv_linear_fwd(const void* x, const void* w, const float* bias, const floa
     p.epi_flags |= EPI_STATS; p.stats_partial = stats_partial;
   }
   p.out_f32 = out_f32; p.bias = bias; p.resid = resid; p.out = y; p.ldd = N; p.split_stride = 0;
-  return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream);
+  return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream, resid, true);
 }
 
 int saicv_linear_dgrad(const void* dy, const void* w, const float* resid, const void* gelu_pre, void* dx,
@@ -250,7 +296,7 @@ int saicv_linear_dgrad(const void* dy, const void* w, const float* resid, const 
   p.epi_flags = (flags & EPI_DIRECT) | (resid ? EPI_RESID : 0) | aux_mode;
   if (gelu_pre && !aligned16(gelu_pre)) return set_error("saicv_linear_dgrad: unaligned aux operand");
   p.out_f32 = out_f32; p.resid = resid; p.resid_bf16 = gelu_pre; p.out = dx; p.ldd = K;
-  return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream);
+  return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream, resid ? (const void*)resid : gelu_pre, resid != nullptr);
 }
 
 int saicv_linear_wgrad(const void* dy, const void* x, float* dw_partial, int M, int N, int K,
@@ -327,7 +373,7 @@ int saicv_conv_dgrad(const void* dy, const void* w, const void* add, void* dx,
   p.g.R = cs->r; p.g.S = cs->s; p.g.cchunks = cs->k / 64; p.g.n_img = cs->n;
   p.epi_flags = add ? EPI_RESID_BF16 : 0; p.resid_bf16 = add; p.out_f32 = 0; p.out = dx; p.ldd = cs->c;
   if (add && !aligned16(add)) return set_error("saicv_conv_dgrad: unaligned `add`");
-  return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream);
+  return dispatch(bn, ta, tb, td, p, (cudaStream_t)stream, add, false);
 }
 
 int saicv_conv_wgrad(const void* dy, const void* x, float* dw_partial, const saicv_conv_shape* cs,

@@ -29,16 +29,23 @@ enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_GELU = 4, EPI_DIRECT = 8, EPI_RESID
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kGemmThreads = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
-constexpr int kStoreBufBytes = 16384;  // 128 rows x 128 B
-constexpr int kSmemBudget = 232448 - 1024 /*align slack*/ - 512 /*barriers*/;
+constexpr int kStoreBufBytes = 16384;  // one staging slice: 128 rows x 128 B
+constexpr int kMaxStoreBufs = 3;       // staging slices per epilogue half (runtime 1..3, GemmParams::store_bufs)
+constexpr int kSmemTotal = 232448;     // dynamic shared memory every launch asks for (227 KB)
+constexpr int kSmemBudget = kSmemTotal - 1024 /*align slack*/ - 512 /*barriers*/;
 
+// The split of shared memory between the operand ring and the epilogue staging slices is a launch
+// parameter (capi_gemm.cu: pick_smem_split): long reductions want >= 4 ring stages and get one slice
+// per half, short reductions (the epilogue-bound 1x1 convolutions, K = 64..256) trade ring stages
+// for 2-3 slices so that a TMA store (and the TMA load of the next aux slice) is never waited for
+// right after it was issued.
 template <int BN>
 struct GemmCfg {
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
   static constexpr int kStagesRaw = (kSmemBudget - 2 * kStoreBufBytes) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;   // upper bound of the ring depth
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStoreBufBytes + 512 + 1024;
+  static constexpr int kSmemBytes = kSmemTotal;
 };
 
 struct ConvGeom {
@@ -72,6 +79,10 @@ struct GemmParams {
   long long ldd;       // leading dimension of D in elements
   long long split_stride;  // elements between split-K partial outputs
   int num_stages;      // smem ring depth actually used (<= GemmCfg::kStages)
+  int store_bufs;      // staging slices per epilogue half (1..kMaxStoreBufs)
+  int aux_tma;         // 1: the aux operand of the epilogue (resid when out_f32, resid_bf16 otherwise) has the
+                       // output's element width and is brought in by TMA (tensor map tmR) INTO the staging
+                       // slice, combined in place and stored from there; 0: per-thread global loads
   float* stats_partial;  // EPI_STATS: [gridDim.x][2][N] per-CTA column sums / sums of squares of the bf16 output
 };
 
@@ -101,7 +112,8 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+                  const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kABytes = BM * BK * 2;
@@ -115,12 +127,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* sA = smem;
   uint8_t* sB = smem + nstages * kABytes;
   uint8_t* sD = smem + nstages * Cfg::kStageBytes;
-  float* sStat = reinterpret_cast<float*>(sD + 2 * kStoreBufBytes);  // [2][N] when EPI_STATS
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sD + 2 * kStoreBufBytes + (do_stats ? ((8 * p.N + 15) & ~15) : 0));
+  const int NB = p.store_bufs;
+  float* sStat = reinterpret_cast<float*>(sD + 2 * NB * kStoreBufBytes);  // [2][N] when EPI_STATS
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sD + 2 * NB * kStoreBufBytes + (do_stats ? ((8 * p.N + 15) & ~15) : 0));
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;   // [2 halves][kMaxStoreBufs]: aux slice landed in staging slice b
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * kMaxStoreBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -129,6 +143,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
+    if (p.aux_tma) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -139,6 +154,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);
     }
+    for (int i = 0; i < 2 * kMaxStoreBufs; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -276,23 +292,50 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp >= 4) {
     // ================================================================ epilogue
     // 8 warps: warp e handles TMEM sub-partition (lanes) e%4 and column half e/4 of every tile, so
-    // two warps drain each 32-lane quadrant concurrently.  Each half owns one 16 KB staging buffer
-    // and its own TMA-store bulk groups.
+    // two warps drain each 32-lane quadrant concurrently.  Each half owns NB 16 KB staging slices
+    // (128 rows x 128 B = 64 bf16 or 32 fp32 columns, 128B-swizzled) used round-robin and its own
+    // TMA-store bulk groups: slice s is written while the store of slice s-1 is still reading.
+    // With aux_tma the half's thread 0 also TMA-loads the aux operand of slice s+LA (LA = max(1, NB-1))
+    // into the slice that store s-1 has released; every thread combines its own row in place.
     const int e = warp - 4;
     const int q = e & 3;
     const int half = e >> 2;
     const int gtid = threadIdx.x - 128 - half * 128;  // 0..127 inside the half
     const int row_in_tile = q * 32 + lane;
+    const int rsw = row_in_tile & 7;                  // 128B-swizzle phase of this thread's staging row
     const uint32_t bar_id = 1 + half;
-    uint8_t* const sbuf = sD + half * kStoreBufBytes;
+    uint8_t* const sbase = sD + half * NB * kStoreBufBytes;
+    uint64_t* const abar = aux_bar + half * kMaxStoreBufs;
     int as = 0;
     uint32_t aphase = 0;
     const bool direct = (p.epi_flags & EPI_DIRECT) != 0;
+    const bool aux_tma = p.aux_tma != 0;
     // chunk (32 columns) range of this half: whole 64-column bf16 slices, or 32-column fp32 slices
     constexpr int NCH = BN / 32;
     const int split_at = p.out_f32 ? (NCH + 1) / 2 : 2 * ((BN / 64 + 1) / 2);
     const int c_begin = half ? split_at : 0;
     const int c_end = half ? NCH : split_at;
+    const int spt = p.out_f32 ? (c_end - c_begin) : ((c_end - c_begin) >> 1);  // slices per tile of this half
+    int bufi = 0;             // staging slice of the current output slice
+    uint32_t aux_phase = 0;   // bit b: parity to wait for on abar[b]
+    // aux prefetch cursor (thread 0 of the half): next slice to request = slice pf_j of work item pf_w
+    long long pf_w = blockIdx.x;
+    int pf_j = 0, pf_b = 0;
+    auto request_aux = [&]() {
+      if (pf_w < total) {
+        const int n_blk2 = (int)(pf_w % num_n);
+        const int m_blk2 = (int)((pf_w / num_n) % num_m);
+        const int col = n_blk2 * BN + (p.out_f32 ? (c_begin + pf_j) * 32 : ((c_begin >> 1) + pf_j) * 64);
+        mbar_expect_tx(&abar[pf_b], kStoreBufBytes);   // rows / columns past the matrix are zero-filled and counted
+        tma_load_3d(&tmR, &abar[pf_b], sbase + pf_b * kStoreBufBytes, col, m_blk2 * BM, 0);
+      }
+      if (++pf_j == spt) { pf_j = 0; pf_w += gridDim.x; }
+      if (++pf_b == NB) pf_b = 0;
+    };
+    if (aux_tma && gtid == 0 && spt > 0) {
+      const int la = NB > 1 ? NB - 1 : 1;
+      for (int i = 0; i < la; ++i) request_aux();
+    }
     if (do_stats) {
       for (int j = threadIdx.x - 128; j < 2 * p.N; j += 256) sStat[j] = 0.f;
       named_bar_sync(3, 256);
@@ -315,6 +358,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
         const int col0 = n0 + c * 32;
+        const int part = p.out_f32 ? 0 : ((c - c_begin) & 1);   // bf16: which 32-column half of the 64-column slice
+        const bool s_begin = p.out_f32 || part == 0;
+        const bool s_end = p.out_f32 || part == 1;
+        uint8_t* const sbuf = sbase + bufi * kStoreBufBytes;
+        uint8_t* const buf = sbuf + row_in_tile * 128;
         // operands of the epilogue are requested before the TMEM load so their latency overlaps it
         float bv = 0.f;
         if ((p.epi_flags & EPI_BIAS) && col0 + lane < p.N) bv = __ldg(p.bias + col0 + lane);
@@ -324,16 +372,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool has_rb = (p.epi_flags & (EPI_RESID_BF16 | EPI_MUL_DGELU | EPI_MUL_DRELU)) && row < p.M;
         float rscale = 1.f;
         if ((p.epi_flags & EPI_ROW_SCALE) && row < p.M) rscale = __ldg(p.row_scale + row / p.rows_per_scale);
-        if (has_rf) {
-          const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ldd + col0);
+        if (!aux_tma) {
+          if (has_rf) {
+            const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ldd + col0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rf[j] = (col0 + 4 * j < p.N) ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (has_rb) {
-          const uint4* rp = reinterpret_cast<const uint4*>(
-              reinterpret_cast<const __nv_bfloat16*>(p.resid_bf16) + row * p.ldd + col0);
+            for (int j = 0; j < 8; ++j) rf[j] = (col0 + 4 * j < p.N) ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (has_rb) {
+            const uint4* rp = reinterpret_cast<const uint4*>(
+                reinterpret_cast<const __nv_bfloat16*>(p.resid_bf16) + row * p.ldd + col0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rb[j] = (col0 + 8 * j < p.N) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < 4; ++j) rb[j] = (col0 + 8 * j < p.N) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+          }
         }
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
@@ -343,6 +393,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (aux_tma) {
+          // the aux slice was TMA-loaded into this staging slice; each thread reads its own (swizzled) row
+          if (s_begin) mbar_wait(&abar[bufi], (aux_phase >> bufi) & 1u);
+          if (p.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rf[j] = *reinterpret_cast<const float4*>(buf + ((j ^ rsw) << 4));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rb[j] = *reinterpret_cast<const uint4*>(buf + (((part * 4 + j) ^ rsw) << 4));
+          }
         }
         float f[32];
 #pragma unroll
@@ -363,28 +424,32 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= rscale;
         }
-        if (has_rf) {
+        if (p.epi_flags & EPI_RESID) {
+          if (aux_tma || has_rf) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            f[4 * j] += rf[j].x; f[4 * j + 1] += rf[j].y; f[4 * j + 2] += rf[j].z; f[4 * j + 3] += rf[j].w;
+            for (int j = 0; j < 8; ++j) {
+              f[4 * j] += rf[j].x; f[4 * j + 1] += rf[j].y; f[4 * j + 2] += rf[j].z; f[4 * j + 3] += rf[j].w;
+            }
           }
         }
-        if (has_rb) {
+        if (p.epi_flags & (EPI_RESID_BF16 | EPI_MUL_DGELU | EPI_MUL_DRELU)) {
+          if (aux_tma || has_rb) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t wv[4] = {rb[j].x, rb[j].y, rb[j].z, rb[j].w};
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t wv[4] = {rb[j].x, rb[j].y, rb[j].z, rb[j].w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float2 ab = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[u]));
-              if (p.epi_flags & EPI_MUL_DGELU) {
-                f[8 * j + 2 * u] *= gelu_erf_grad(ab.x);
-                f[8 * j + 2 * u + 1] *= gelu_erf_grad(ab.y);
-              } else if (p.epi_flags & EPI_MUL_DRELU) {   // resid_bf16 = ReLU output: pass the gradient where it is > 0
-                f[8 * j + 2 * u] = ab.x > 0.f ? f[8 * j + 2 * u] : 0.f;
-                f[8 * j + 2 * u + 1] = ab.y > 0.f ? f[8 * j + 2 * u + 1] : 0.f;
-              } else {
-                f[8 * j + 2 * u] += ab.x;
-                f[8 * j + 2 * u + 1] += ab.y;
+              for (int u = 0; u < 4; ++u) {
+                const float2 ab = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[u]));
+                if (p.epi_flags & EPI_MUL_DGELU) {
+                  f[8 * j + 2 * u] *= gelu_erf_grad(ab.x);
+                  f[8 * j + 2 * u + 1] *= gelu_erf_grad(ab.y);
+                } else if (p.epi_flags & EPI_MUL_DRELU) {   // resid_bf16 = ReLU output: pass the gradient where it is > 0
+                  f[8 * j + 2 * u] = ab.x > 0.f ? f[8 * j + 2 * u] : 0.f;
+                  f[8 * j + 2 * u + 1] = ab.y > 0.f ? f[8 * j + 2 * u + 1] : 0.f;
+                } else {
+                  f[8 * j + 2 * u] += ab.x;
+                  f[8 * j + 2 * u + 1] += ab.y;
+                }
               }
             }
           }
@@ -408,45 +473,31 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                  pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
             }
           }
-        } else if (p.out_f32) {
-          // one 128 B (32 x fp32) slice per TMA store
-          if (gtid == 0) tma_store_wait_read<0>();
-          named_bar_sync(bar_id, 128);
-          uint8_t* buf = sbuf + row_in_tile * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(buf + ((j ^ (row_in_tile & 7)) << 4)) =
-                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          fence_proxy_async_smem();
-          named_bar_sync(bar_id, 128);
-          if (gtid == 0) {
-            if (col0 < p.N) {
-              asm volatile(
-                  "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                      reinterpret_cast<uint64_t>(&tmD)),
-                  "r"(smem_u32(sbuf)), "r"(col0), "r"(m0), "r"(split)
-                  : "memory");
-            }
-            tma_store_commit();
-          }
         } else {
-          // bf16: two 32-column chunks make one 128 B (64 x bf16) slice
-          const int part = (c - c_begin) & 1;
-          if (part == 0) {
-            if (gtid == 0) tma_store_wait_read<0>();
+          if (s_begin && !aux_tma) {
+            // the store that last read this staging slice (NB slices ago) must have drained it
+            if (gtid == 0) tma_store_wait_read_n(NB - 1);
             named_bar_sync(bar_id, 128);
           }
-          uint8_t* buf = sbuf + row_in_tile * 128;
+          if (p.out_f32) {
+            // one 128 B (32 x fp32) slice per TMA store
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(buf + (((part * 4 + j) ^ (row_in_tile & 7)) << 4)) =
-                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-          if (part == 1) {
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(buf + ((j ^ rsw) << 4)) =
+                  make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            // bf16: two 32-column chunks make one 128 B (64 x bf16) slice
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(buf + (((part * 4 + j) ^ rsw) << 4)) =
+                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+          }
+          if (s_end) {
             fence_proxy_async_smem();
             named_bar_sync(bar_id, 128);
+            const int scol = p.out_f32 ? col0 : col0 - 32;
             if (gtid == 0) {
-              const int scol = n0 + (c >> 1) * 64;
               if (scol < p.N) {
                 asm volatile(
                     "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
@@ -455,6 +506,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     : "memory");
               }
               tma_store_commit();
+              if (aux_tma) {
+                // the slice that store s-1 read becomes the landing buffer of aux slice s + LA
+                tma_store_wait_read_n(NB > 1 ? 1 : 0);
+                request_aux();
+              }
             }
             if (do_stats) {
               // BatchNorm statistics of the slice just staged (the bf16 values as stored), read back
@@ -488,7 +544,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], o);
                 }
               }
-              const int gcol = n0 + (c >> 1) * 64 + wq * 16 + piece * 4;
+              const int gcol = scol + wq * 16 + piece * 4;
               if (lane < 4 && gcol < p.N) {  // N % 8 == 0: the 4 columns are valid together
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -497,6 +553,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
               }
             }
+            aux_phase ^= (1u << bufi);
+            if (++bufi == NB) bufi = 0;
           }
         }
       }

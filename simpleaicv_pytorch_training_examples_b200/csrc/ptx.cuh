@@ -91,6 +91,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 3-D tiled load: coordinates innermost first.
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // 4-D tiled load: coordinates innermost first.
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
                                             int c3) {
@@ -126,6 +134,12 @@ __device__ __forceinline__ void tma_store_commit() {
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// runtime count (0..2) of bulk groups that may still be reading shared memory
+__device__ __forceinline__ void tma_store_wait_read_n(int n) {
+  if (n <= 0) tma_store_wait_read<0>();
+  else if (n == 1) tma_store_wait_read<1>();
+  else tma_store_wait_read<2>();
 }
 template <int N>
 __device__ __forceinline__ void tma_store_wait() {

@@ -46,9 +46,19 @@ class GraphedTrainStep:
         self.optimizer.zero_grad()
         return loss.detach()
 
+    def _replay(self):
+        # fused optimizers (optim.py) read their hyper-parameters from a pinned table through a copy node of the graph:
+        # per-iteration learning rates / AdamW bias corrections are a host write before the launch
+        sync = getattr(self.optimizer, 'sync_hyper', None)
+        if sync is not None:
+            sync()
+        self.graph.replay()
+        if sync is not None:
+            self.optimizer.after_replay()
+
     def replay(self):
         """Replays the step on the batch already in the static buffers; returns the loss tensor."""
-        self.graph.replay()
+        self._replay()
         return self.static_loss
 
     def __call__(self, x, y):
@@ -56,7 +66,7 @@ class GraphedTrainStep:
         (valid until the next call)."""
         self.static_x.copy_(x, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
-        self.graph.replay()
+        self._replay()
         return self.static_loss
 
 
@@ -113,5 +123,10 @@ class GraphedSplitStep:
                 s.zero_()
             else:
                 s.copy_(g)
+        sync = getattr(self.optimizer, 'sync_hyper', None)
+        if sync is not None:
+            sync()
         self.graph_bwd.replay()
+        if sync is not None:
+            self.optimizer.after_replay()
         return loss.detach()

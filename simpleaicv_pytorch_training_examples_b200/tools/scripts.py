@@ -69,7 +69,10 @@ def train_classification(train_loader, model, criterion, optimizer, scheduler, e
             if getattr(config, 'clip_grad_value', 0) and config.clip_grad_value > 0:
                 torch.nn.utils.clip_grad_value_(model.parameters(), config.clip_grad_value)
             if getattr(config, 'clip_max_norm', 0) and config.clip_max_norm > 0:
-                torch.nn.utils.clip_grad_norm_(model.parameters(), config.clip_max_norm)
+                if hasattr(optimizer, 'clip_grad_norm'):    # fused: coefficient stays on the device, applied inside step()
+                    optimizer.clip_grad_norm(config.clip_max_norm)
+                else:
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), config.clip_max_norm)
             optimizer.step()
             optimizer.zero_grad()
             if getattr(config, 'use_ema_model', False):
@@ -133,7 +136,10 @@ def train_epoch_with_loss_terms(train_loader, model, criterion, optimizer, sched
             if getattr(config, 'clip_grad_value', 0) and config.clip_grad_value > 0:
                 torch.nn.utils.clip_grad_value_(model.parameters(), config.clip_grad_value)
             if getattr(config, 'clip_max_norm', 0) and config.clip_max_norm > 0:
-                torch.nn.utils.clip_grad_norm_(model.parameters(), config.clip_max_norm)
+                if hasattr(optimizer, 'clip_grad_norm'):    # fused: coefficient stays on the device, applied inside step()
+                    optimizer.clip_grad_norm(config.clip_max_norm)
+                else:
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), config.clip_max_norm)
             optimizer.step()
             optimizer.zero_grad()
             if getattr(config, 'use_ema_model', False):

@@ -109,12 +109,24 @@ def build_optimizer(config, model):
         descr.setdefault(key, []).append(r['name'])
     param_groups = [{'params': ps, 'weight_decay': k[0], 'lr': k[1] * k[2]} for k, ps in groups.items()]
     info = [{'name': descr[k], 'weight_decay': k[0], 'lr': k[1], 'lr_scale': k[2]} for k in groups]
+    # fused multi-tensor step (optim.py) whenever the parameters live on the GPU; 'fused': False in the
+    # optimizer config keeps torch.optim (the reference's tools/utils.py:581-600)
+    fused = bool(opt.get('fused', True)) and len(rows) > 0 and all(r['param'].is_cuda for r in rows)
     if name == 'SGD':
-        optimizer = torch.optim.SGD(param_groups, lr=opt['lr'], momentum=opt['momentum'],
-                                    nesterov=opt.get('nesterov', False))
+        if fused:
+            from ..optim import FusedSGD
+            optimizer = FusedSGD(param_groups, lr=opt['lr'], momentum=opt['momentum'], nesterov=opt.get('nesterov', False)).attach(model)
+        else:
+            optimizer = torch.optim.SGD(param_groups, lr=opt['lr'], momentum=opt['momentum'],
+                                        nesterov=opt.get('nesterov', False))
     else:
-        optimizer = torch.optim.AdamW(param_groups, lr=opt['lr'], betas=(opt.get('beta1', 0.9), opt.get('beta2', 0.999)),
-                                      eps=opt.get('eps', 1e-8), capturable=bool(opt.get('capturable', False)))
+        if fused:
+            from ..optim import FusedAdamW
+            optimizer = FusedAdamW(param_groups, lr=opt['lr'], betas=(opt.get('beta1', 0.9), opt.get('beta2', 0.999)),
+                                   eps=opt.get('eps', 1e-8)).attach(model)
+        else:
+            optimizer = torch.optim.AdamW(param_groups, lr=opt['lr'], betas=(opt.get('beta1', 0.9), opt.get('beta2', 0.999)),
+                                          eps=opt.get('eps', 1e-8), capturable=bool(opt.get('capturable', False)))
     return optimizer, info
 
 

@@ -74,6 +74,40 @@ def test_linear_epilogue_rowscale_and_dgelu():
     _close(dx, uf.grad, 1e-2, 1e-2, 'dgelu epilogue')
 
 
+@pytest.mark.parametrize('tune', ['', '0:0:1', '0:0:2', '0:0:3', '128:3:3', '64:2:2', '192:0:2', 'legacy'])
+@pytest.mark.parametrize('M,N,K', [(300, 200, 64), (5000, 768, 256), (1111, 1000, 1024)])
+def test_epilogue_aux_operand_by_tma(M, N, K, tune, monkeypatch):
+    """The aux operand of the epilogue (fp32 residual / bf16 addend, ReLU mask, GELU pre-activation) is TMA-loaded into the
+    staging slices (gemm_sm100.cuh, aux_tma) with 1-3 slices per half and any tile width: ragged M and N, several tiles per
+    CTA so the slices wrap, compared with torch and with the per-thread-load path ('legacy')."""
+    ops = _ops()
+    if tune == 'legacy':
+        monkeypatch.setenv('SAICV_GEMM_NO_AUX_TMA', '1')
+    elif tune:
+        monkeypatch.setenv('SAICV_GEMM_TUNE', tune)
+    x, w = _bf(M, K, seed=1), _bf(N, K, scale=K ** -0.5, seed=2)
+    bias, resid = torch.randn(N, device='cuda'), torch.randn(M, N, device='cuda')
+    lin = x.float() @ w.float().t() + bias
+    y = ops.linear_fwd(x, w, bias=bias, resid=resid, out_f32=True)
+    _close(y, lin + resid, 1e-4, 1e-4, f'fp32 residual by TMA [{tune}]')
+    inplace = resid.clone()
+    ops.linear_fwd(x, w, bias=bias, resid=inplace, out_f32=True, out=inplace)
+    _close(inplace, lin + resid, 1e-4, 1e-4, f'fp32 residual in place [{tune}]')
+    dy, wd = _bf(M, K, seed=3), _bf(K, N, scale=K ** -0.5, seed=4)      # dx[M, N] = dy[M, K] wd[K, N]
+    aux = _bf(M, N, scale=2.0, seed=5)
+    base = dy.float() @ wd.float()
+    _close(ops.linear_dgrad(dy, wd, add=aux), base + aux.float(), 1e-2, 1e-2, f'bf16 addend [{tune}]')
+    _close(ops.linear_dgrad(dy, wd, relu_out=aux), base * (aux.float() > 0), 1e-2, 1e-2, f'ReLU mask [{tune}]')
+    uf = aux.float().requires_grad_(True)
+    F.gelu(uf).backward(base)
+    _close(ops.linear_dgrad(dy, wd, gelu_pre=aux), uf.grad, 1e-2, 1e-2, f'dGELU [{tune}]')
+    r32 = torch.randn(M, N, device='cuda')
+    _close(ops.linear_dgrad(dy, wd, resid=r32, out_f32=True), base + r32, 1e-4, 1e-4, f'fp32 chained gradient [{tune}]')
+    # plain outputs through 1-3 staging slices (no aux): bf16 and fp32
+    _close(ops.linear_fwd(x, w, bias=bias), lin, 1e-2, 1e-2, f'plain bf16 [{tune}]')
+    _close(ops.linear_fwd(x, w, bias=bias, out_f32=True), lin, 1e-4, 1e-4, f'plain fp32 [{tune}]')
+
+
 @pytest.mark.parametrize('M,N,K', [(256, 128, 64), (300, 1000, 2048), (1024, 3072, 768)])
 def test_linear_dgrad(M, N, K):
     ops = _ops()
