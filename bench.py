@@ -555,6 +555,29 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
 
     e2e_loop(2)
     e2e_ms = timed(lambda: e2e_loop(steps), 1) / steps
+
+    # the same loop with the input-pipeline edge of SURVEY.md 8 f3: the host batch is the decoder's uint8 [B, H, W, 3] pixels
+    # (classification.common.Uint8ClassificationCollater), a quarter of the fp32 batch's bytes on the host link; the
+    # prefetcher normalises it into the fp32 NCHW batch on the device (csrc/capi_input.cu), then the same step runs
+    e2e_u8 = None
+    if model_name in ('resnet50', 'vit_base_patch16') and x_host.dim() == 4:
+        g8 = torch.Generator().manual_seed(4321 + rank)
+        x8 = torch.randint(0, 256, (B, x_host.shape[2], x_host.shape[3], 3), dtype=torch.uint8, generator=g8).pin_memory()
+        norm = ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+
+        def e2e_u8_loop(k):
+            host_batches = ({'image': x8, 'label': y_host} for _ in range(k))
+            for batch in tutils.CudaPrefetcher(host_batches, dev, copy_streams=args.prefetch_streams, normalize=norm):
+                if graphed is not None:
+                    graphed(batch['image'], batch['label']).item()
+                else:
+                    step(batch['image'], batch['label']).item()
+
+        e2e_u8_loop(2)
+        u8_ms = timed(lambda: e2e_u8_loop(steps), 1) / steps
+        e2e_u8 = {'value': B * world / (u8_ms / 1e3), 'unit': 'images/s', 'ms_per_step': u8_ms,
+                  'h2d_bytes_per_step': (x8.numel() + y_host.numel() * y_host.element_size()) * world, 'd2h_bytes_per_step': 4 * world,
+                  'input': 'uint8 [B,H,W,3] pinned host batch, ToTensor+Normalize+permute on the device (bit-identical to the host pipeline)'}
     graph_ddp_check = None
     if world > 1 and graphed is not None:
         # every rank trained on its own batches: parameters stay identical across ranks only if the captured all-reduces ran
@@ -588,7 +611,7 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
                        'd2h_bytes_per_step': 4 * world, 'mode': graph_note},
                'gpu_launches': int(launches), 'roofline': roof, 'clocks': clocks, 'workload': WORKLOADS[model_name],
                'ddp_check': ddp_check, 'graph_ddp_check': graph_ddp_check, 'eager_ms_per_step': eager_ms_step, 'per_gpu_batch': B, 'timed_steps': steps,
-               'value_mode': graph_note}
+               'value_mode': graph_note, 'e2e_uint8_input': e2e_u8}
     del model, net, opt
     torch.cuda.empty_cache()
     return rec
@@ -631,9 +654,10 @@ def run_b200(args, rank, world, local_rank):
         line['ddp_check'] = main['ddp_check']
     if main.get('graph_ddp_check'):
         line['graph_ddp_check'] = main['graph_ddp_check']
-    SUB = ('metric', 'value', 'unit', 'ms_per_step', 'eager_ms_per_step', 'value_mode', 'e2e', 'gpu_launches', 'roofline', 'clocks',
-           'workload', 'per_gpu_batch', 'timed_steps')
+    SUB = ('metric', 'value', 'unit', 'ms_per_step', 'eager_ms_per_step', 'value_mode', 'e2e', 'e2e_uint8_input', 'gpu_launches', 'roofline',
+           'clocks', 'workload', 'per_gpu_batch', 'timed_steps')
     line['eager_ms_per_step'], line['value_mode'] = main['eager_ms_per_step'], main['value_mode']
+    line['e2e_uint8_input'] = main.get('e2e_uint8_input')
     if other is not None:
         name = 'vit_base_patch16' if args.model == 'resnet50' else 'resnet50'
         line[name] = {k: other[k] for k in SUB}

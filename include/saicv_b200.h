@@ -403,6 +403,13 @@ int saicv_multi_tensor_adamw(const void* tensors, const int* chunk_tensor, const
 int saicv_multi_tensor_clip_coef(const void* tensors, const int* chunk_tensor, const int* chunk_index, int n_chunks,
                                  float max_norm, float* partial, float* clip, void* stream);
 
+/* ---- input-pipeline edge (csrc/capi_input.cu) ---------------------------------------------------------
+ * out fp32 [n][3][h][w] = (float(in uint8 [n][h][w][3]) / 255 - mean[c]) / std[c]: ToTensor + Normalize of
+ * classification/common.py:228-248 followed by the collater's NHWC -> NCHW permute (:645-665), on the device, bit-identical
+ * to the host arithmetic (IEEE divisions in the same order).  mean3 / std3 are HOST pointers to 3 floats. */
+int saicv_u8_nhwc_to_nchw_norm(const void* in, float* out, int n, int h, int w, const float* mean3, const float* std3,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

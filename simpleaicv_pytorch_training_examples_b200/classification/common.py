@@ -1,7 +1,43 @@
 """Host-side helpers of the classification hot path with the reference's names
-(SimpleAICV/classification/common.py:668-685 AverageMeter, :688-709 AccMeter, :843-881 get_amp_type).
-Transforms / collaters / datasets are CPU data code and out of scope."""
+(SimpleAICV/classification/common.py:668-685 AverageMeter, :688-709 AccMeter, :843-881 get_amp_type) and the
+input-pipeline edge of SURVEY.md 8 f3: ``Uint8ClassificationCollater`` + ``DeviceNormalize`` move the batch over PCIe as
+uint8 pixels and normalise on the device.  The per-sample transforms / datasets stay CPU data code."""
+import numpy as np
 import torch
+
+
+class Uint8ClassificationCollater:
+    """Counterpart of ClassificationCollater (common.py:645-665) for samples whose 'image' is still the decoder's uint8
+    [H, W, 3] array (i.e. the transform list ends BEFORE TorchMeanStdNormalize / Normalize): stacks into ONE pinned uint8
+    [B, H, W, 3] tensor (a quarter of the fp32 batch's bytes on the host link) and int64 labels.  ``DeviceNormalize`` (or
+    tools.utils.CudaPrefetcher(normalize=...)) finishes the reference's arithmetic on the GPU."""
+
+    def __init__(self, pin_memory=True):
+        self.pin_memory = pin_memory
+
+    def __call__(self, data):
+        images = np.stack([np.ascontiguousarray(s['image']) for s in data])
+        assert images.dtype == np.uint8 and images.ndim == 4 and images.shape[3] == 3, 'expects uint8 [H, W, 3] images'
+        labels = torch.from_numpy(np.array([s['label'] for s in data]).astype(np.float32)).long()
+        images = torch.from_numpy(images)
+        if self.pin_memory and torch.cuda.is_available():
+            images, labels = images.pin_memory(), labels.pin_memory()
+        return {'image': images, 'label': labels}
+
+
+class DeviceNormalize:
+    """(x / 255 - mean) / std and NHWC -> NCHW on the device (csrc/capi_input.cu): TorchMeanStdNormalize
+    (common.py:228-248; mean / std given) or Normalize (:190-206; mean 0, std 1 -> x / 255) followed by the collater's
+    permute, bit-identical to the host pipeline.  Raises on CPU tensors: there is no host fallback."""
+
+    def __init__(self, mean=(0., 0., 0.), std=(1., 1., 1.)):
+        self.mean, self.std = tuple(float(v) for v in mean), tuple(float(v) for v in std)
+
+    def __call__(self, images_u8, out=None):
+        from .. import ops
+        if not images_u8.is_cuda:
+            raise RuntimeError('DeviceNormalize runs on the GPU (uint8 [B, H, W, 3] device tensor expected)')
+        return ops.u8_normalize(images_u8, self.mean, self.std, out=out)
 
 
 class AverageMeter:

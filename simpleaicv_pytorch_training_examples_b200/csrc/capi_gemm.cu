@@ -157,13 +157,13 @@ void pick_smem_split(const GemmParams& p, int stat_bytes, int* stages_out, int* 
   *nb_out = nb;
 }
 
-template <int BN>
+template <int BN, int VAR>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& r, const GemmParams& p,
            cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_sm100_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_sm100_kernel<BN, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
     attr_set = true;
@@ -177,7 +177,7 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, con
   if (stages < 2) return set_error("gemm_sm100_kernel<%d>: %d bytes of statistics do not fit in shared memory", BN, stat_bytes);
   const_cast<GemmParams&>(p).num_stages = stages;
   const_cast<GemmParams&>(p).store_bufs = nb;
-  gemm_sm100_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a, b, d, r, p);
+  gemm_sm100_kernel<BN, VAR><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a, b, d, r, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm_sm100_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
   count_launch(1);
@@ -210,12 +210,27 @@ int dispatch(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorM
     if (!encode_out(&r, aux, aux_f32, p.N, p.M, p.ldd, 1, 0)) return 2;
     p.aux_tma = 1;
   }
-  switch (bn) {
-    case 64: return launch<64>(a, b, d, r, p, st);
-    case 128: return launch<128>(a, b, d, r, p, st);
-    case 192: return launch<192>(a, b, d, r, p, st);
-    default: return launch<256>(a, b, d, r, p, st);
+  // compile-time epilogue variant (gemm_sm100.cuh GemmVariant); SAICV_GEMM_FULL_VARIANT=1 forces the run-time one
+  int var = VAR_FULL;
+  if (!getenv("SAICV_GEMM_FULL_VARIANT")) {
+    if (p.aux_tma && !(p.epi_flags & ~GemmVariant<VAR_AUX>::kMask)) var = VAR_AUX;
+    else if (!p.aux_tma && !p.out_f32 && !(p.epi_flags & ~GemmVariant<VAR_PLAIN_BF16>::kMask)) var = VAR_PLAIN_BF16;
+    else if (!p.aux_tma && p.out_f32 && !(p.epi_flags & ~GemmVariant<VAR_PLAIN_F32>::kMask)) var = VAR_PLAIN_F32;
   }
+#define SAICV_LAUNCH_BN(BN_)                                                         \
+  switch (var) {                                                                     \
+    case VAR_PLAIN_BF16: return launch<BN_, VAR_PLAIN_BF16>(a, b, d, r, p, st);      \
+    case VAR_PLAIN_F32: return launch<BN_, VAR_PLAIN_F32>(a, b, d, r, p, st);        \
+    case VAR_AUX: return launch<BN_, VAR_AUX>(a, b, d, r, p, st);                    \
+    default: return launch<BN_, VAR_FULL>(a, b, d, r, p, st);                        \
+  }
+  switch (bn) {
+    case 64: SAICV_LAUNCH_BN(64)
+    case 128: SAICV_LAUNCH_BN(128)
+    case 192: SAICV_LAUNCH_BN(192)
+    default: SAICV_LAUNCH_BN(256)
+  }
+#undef SAICV_LAUNCH_BN
 }
 
 }  // namespace

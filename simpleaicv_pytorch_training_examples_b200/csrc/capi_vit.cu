@@ -9,6 +9,7 @@
 #include <math_constants.h>
 
 #include "../../include/saicv_b200.h"
+#include "gelu_math.cuh"
 #include "host_util.h"
 
 namespace saicv {
@@ -161,24 +162,9 @@ __global__ void ln_fold_kernel(const float* __restrict__ partials, float* __rest
 }
 
 // ----------------------------------------------------------------------------- GELU (exact, erf)
-// erf through the Abramowitz-Stegun 7.1.26 rational approximation (|error| < 1.5e-7, far below the bf16 resolution of
-// the stored result) and ONE __expf shared between erf's exp(-z^2) (z = x / sqrt 2) and the Gaussian density of gelu':
-// libdevice erff costs ~40 instructions per element, which made these streaming kernels compute bound (3.7 TB/s);
-// the same formulation is used by the GEMM epilogues (gemm_sm100.cuh gelu_terms).
-__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& pdf) {
-  const float e = __expf(-0.5f * x * x);
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, 1.0f + 0.3275911f * z);
-  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-  const float erf_abs = 1.0f - poly * e;
-  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
-  pdf = 0.3989422804014327f * e;
-}
-__device__ __forceinline__ float gelu_val(float x) {
-  float cdf, pdf;
-  gelu_terms(x, cdf, pdf);
-  return x * cdf;
-}
+// gelu_terms (gelu_math.cuh): A&S 7.1.26 erf with one ex2 and one rcp MUFU per element; libdevice erff costs ~40
+// instructions per element, which made these streaming kernels compute bound.
+__device__ __forceinline__ float gelu_val(float x) { return gelu_erf(x); }
 __global__ void gelu_fwd_kernel(const uint4* __restrict__ u, uint4* __restrict__ h, long long nvec) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const uint4 v = u[i];
@@ -191,11 +177,7 @@ __global__ void gelu_fwd_kernel(const uint4* __restrict__ u, uint4* __restrict__
     h[i] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
-__device__ __forceinline__ float gelu_grad(float x) {
-  float cdf, pdf;
-  gelu_terms(x, cdf, pdf);
-  return cdf + x * pdf;
-}
+__device__ __forceinline__ float gelu_grad(float x) { return gelu_erf_grad(x); }
 // du = dh * gelu'(u)
 __global__ void gelu_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ u, uint4* __restrict__ du,
                                 long long nvec) {

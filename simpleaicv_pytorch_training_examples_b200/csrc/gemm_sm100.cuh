@@ -17,6 +17,7 @@
 //   B_MN2D   B is stored [K, N]                                  (weights for dgrad, x for wgrad)
 //   B_IM2COL B is an NHWC tensor read with TMA im2col, [pixels, C] (wgrad of a conv)
 #pragma once
+#include "gelu_math.cuh"
 #include "ptx.cuh"
 
 namespace saicv {
@@ -86,30 +87,27 @@ struct GemmParams {
   float* stats_partial;  // EPI_STATS: [gridDim.x][2][N] per-CTA column sums / sums of squares of the bf16 output
 };
 
-// Exact-erf GELU evaluated with the Abramowitz-Stegun 7.1.26 rational approximation of erf
-// (|error| < 1.5e-7, far below the bf16 resolution of the stored result) and one __expf:
-// exp(-z^2) with z = x/sqrt(2) is exp(-x^2/2), shared with the Gaussian density of gelu'.
-__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& pdf) {
-  const float e = __expf(-0.5f * x * x);
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, 1.0f + 0.3275911f * z);
-  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-  const float erf_abs = 1.0f - poly * e;            // erf(|x|/sqrt2)
-  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));      // Phi(x)
-  pdf = 0.3989422804014327f * e;                    // phi(x)
-}
-__device__ __forceinline__ float gelu_erf(float x) {
-  float cdf, pdf;
-  gelu_terms(x, cdf, pdf);
-  return x * cdf;
-}
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf, pdf;
-  gelu_terms(x, cdf, pdf);
-  return cdf + x * pdf;
-}
+// Kernel variants: the epilogue's feature set is a compile-time mask, so that the common launches run a compact
+// instruction stream.  (ncu, profiles/r02_gemm_epilogue_ncu.md: with every feature a run-time branch the 128 x 256 x 64
+// tiles of the 1x1 convolutions executed ~200 warp instructions per 32-column chunk, a third of the issue slots were
+// lost to branch resolution and instruction-cache misses in the 10 k-instruction kernel, and the epilogue - not HBM -
+// set the pace.)
+//   VAR_FULL        every flag / output type at run time (GELU forward, EPI_DIRECT, per-thread aux loads)
+//   VAR_PLAIN_BF16  bf16 output, optional bias / ReLU / BatchNorm statistics       (conv fprop, plain dgrad, Linear)
+//   VAR_PLAIN_F32   fp32 output, optional bias                                       (split-K weight gradients, fp32 Linear)
+//   VAR_AUX         aux operand by TMA (fp32 residual, bf16 addend / ReLU mask / GELU pre-activation), bias, row scale
+enum : int { VAR_FULL = 0, VAR_PLAIN_BF16 = 1, VAR_PLAIN_F32 = 2, VAR_AUX = 3 };
+template <int VAR>
+struct GemmVariant {
+  static constexpr int kMask = VAR == VAR_FULL ? 0x7fffffff
+                               : VAR == VAR_PLAIN_BF16 ? (EPI_BIAS | EPI_RELU | EPI_STATS)
+                               : VAR == VAR_PLAIN_F32 ? EPI_BIAS
+                               : (EPI_BIAS | EPI_ROW_SCALE | EPI_RESID | EPI_RESID_BF16 | EPI_MUL_DGELU | EPI_MUL_DRELU);
+  static constexpr int kOut = VAR == VAR_PLAIN_BF16 ? 1 : VAR == VAR_PLAIN_F32 ? 2 : 0;   // 0: run time, 1: bf16, 2: fp32
+  static constexpr int kAux = VAR == VAR_FULL ? 0 : VAR == VAR_AUX ? 2 : 1;                // 0: run time, 1: never, 2: always by TMA
+};
 
-template <int BN>
+template <int BN, int VAR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -122,8 +120,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  using V = GemmVariant<VAR>;
+  const int flags = p.epi_flags & V::kMask;          // bits outside the variant's mask are known zeros
+  const bool out_f32 = V::kOut == 0 ? (p.out_f32 != 0) : (V::kOut == 2);
   const int nstages = p.num_stages;
-  const bool do_stats = (p.epi_flags & EPI_STATS) != 0;
+  const bool do_stats = (flags & EPI_STATS) != 0;
   uint8_t* sA = smem;
   uint8_t* sB = smem + nstages * kABytes;
   uint8_t* sD = smem + nstages * Cfg::kStageBytes;
@@ -143,7 +144,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
-    if (p.aux_tma) tma_prefetch_desc(&tmR);
+    if (V::kAux != 1 && p.aux_tma) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -308,14 +309,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* const abar = aux_bar + half * kMaxStoreBufs;
     int as = 0;
     uint32_t aphase = 0;
-    const bool direct = (p.epi_flags & EPI_DIRECT) != 0;
-    const bool aux_tma = p.aux_tma != 0;
+    const bool direct = (flags & EPI_DIRECT) != 0;
+    const bool aux_tma = V::kAux == 0 ? (p.aux_tma != 0) : (V::kAux == 2);
     // chunk (32 columns) range of this half: whole 64-column bf16 slices, or 32-column fp32 slices
     constexpr int NCH = BN / 32;
-    const int split_at = p.out_f32 ? (NCH + 1) / 2 : 2 * ((BN / 64 + 1) / 2);
+    const int split_at = out_f32 ? (NCH + 1) / 2 : 2 * ((BN / 64 + 1) / 2);
     const int c_begin = half ? split_at : 0;
     const int c_end = half ? NCH : split_at;
-    const int spt = p.out_f32 ? (c_end - c_begin) : ((c_end - c_begin) >> 1);  // slices per tile of this half
+    const int spt = out_f32 ? (c_end - c_begin) : ((c_end - c_begin) >> 1);  // slices per tile of this half
     int bufi = 0;             // staging slice of the current output slice
     uint32_t aux_phase = 0;   // bit b: parity to wait for on abar[b]
     // aux prefetch cursor (thread 0 of the half): next slice to request = slice pf_j of work item pf_w
@@ -325,7 +326,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (pf_w < total) {
         const int n_blk2 = (int)(pf_w % num_n);
         const int m_blk2 = (int)((pf_w / num_n) % num_m);
-        const int col = n_blk2 * BN + (p.out_f32 ? (c_begin + pf_j) * 32 : ((c_begin >> 1) + pf_j) * 64);
+        const int col = n_blk2 * BN + (out_f32 ? (c_begin + pf_j) * 32 : ((c_begin >> 1) + pf_j) * 64);
         mbar_expect_tx(&abar[pf_b], kStoreBufBytes);   // rows / columns past the matrix are zero-filled and counted
         tma_load_3d(&tmR, &abar[pf_b], sbase + pf_b * kStoreBufBytes, col, m_blk2 * BM, 0);
       }
@@ -358,20 +359,20 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
         const int col0 = n0 + c * 32;
-        const int part = p.out_f32 ? 0 : ((c - c_begin) & 1);   // bf16: which 32-column half of the 64-column slice
-        const bool s_begin = p.out_f32 || part == 0;
-        const bool s_end = p.out_f32 || part == 1;
+        const int part = out_f32 ? 0 : ((c - c_begin) & 1);   // bf16: which 32-column half of the 64-column slice
+        const bool s_begin = out_f32 || part == 0;
+        const bool s_end = out_f32 || part == 1;
         uint8_t* const sbuf = sbase + bufi * kStoreBufBytes;
         uint8_t* const buf = sbuf + row_in_tile * 128;
         // operands of the epilogue are requested before the TMEM load so their latency overlaps it
         float bv = 0.f;
-        if ((p.epi_flags & EPI_BIAS) && col0 + lane < p.N) bv = __ldg(p.bias + col0 + lane);
+        if ((flags & EPI_BIAS) && col0 + lane < p.N) bv = __ldg(p.bias + col0 + lane);
         float4 rf[8];
         uint4 rb[4];
-        const bool has_rf = (p.epi_flags & EPI_RESID) && row < p.M;
-        const bool has_rb = (p.epi_flags & (EPI_RESID_BF16 | EPI_MUL_DGELU | EPI_MUL_DRELU)) && row < p.M;
+        const bool has_rf = (flags & EPI_RESID) && row < p.M;
+        const bool has_rb = (flags & (EPI_RESID_BF16 | EPI_MUL_DGELU | EPI_MUL_DRELU)) && row < p.M;
         float rscale = 1.f;
-        if ((p.epi_flags & EPI_ROW_SCALE) && row < p.M) rscale = __ldg(p.row_scale + row / p.rows_per_scale);
+        if ((flags & EPI_ROW_SCALE) && row < p.M) rscale = __ldg(p.row_scale + row / p.rows_per_scale);
         if (!aux_tma) {
           if (has_rf) {
             const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ldd + col0);
@@ -397,7 +398,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (aux_tma) {
           // the aux slice was TMA-loaded into this staging slice; each thread reads its own (swizzled) row
           if (s_begin) mbar_wait(&abar[bufi], (aux_phase >> bufi) & 1u);
-          if (p.out_f32) {
+          if (out_f32) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) rf[j] = *reinterpret_cast<const float4*>(buf + ((j ^ rsw) << 4));
           } else {
@@ -408,23 +409,23 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.epi_flags & EPI_BIAS) {
+        if (flags & EPI_BIAS) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, bv, j);
         }
-        if (p.epi_flags & EPI_GELU) {
+        if (flags & EPI_GELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
         }
-        if (p.epi_flags & EPI_RELU) {
+        if (flags & EPI_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        if (p.epi_flags & EPI_ROW_SCALE) {
+        if (flags & EPI_ROW_SCALE) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= rscale;
         }
-        if (p.epi_flags & EPI_RESID) {
+        if (flags & EPI_RESID) {
           if (aux_tma || has_rf) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -432,7 +433,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         }
-        if (p.epi_flags & (EPI_RESID_BF16 | EPI_MUL_DGELU | EPI_MUL_DRELU)) {
+        if (flags & (EPI_RESID_BF16 | EPI_MUL_DGELU | EPI_MUL_DRELU)) {
           if (aux_tma || has_rb) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -440,10 +441,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const float2 ab = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[u]));
-                if (p.epi_flags & EPI_MUL_DGELU) {
+                if (flags & EPI_MUL_DGELU) {
                   f[8 * j + 2 * u] *= gelu_erf_grad(ab.x);
                   f[8 * j + 2 * u + 1] *= gelu_erf_grad(ab.y);
-                } else if (p.epi_flags & EPI_MUL_DRELU) {   // resid_bf16 = ReLU output: pass the gradient where it is > 0
+                } else if (flags & EPI_MUL_DRELU) {   // resid_bf16 = ReLU output: pass the gradient where it is > 0
                   f[8 * j + 2 * u] = ab.x > 0.f ? f[8 * j + 2 * u] : 0.f;
                   f[8 * j + 2 * u + 1] = ab.y > 0.f ? f[8 * j + 2 * u + 1] : 0.f;
                 } else {
@@ -456,7 +457,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (direct) {
           if (row < p.M) {
-            if (p.out_f32) {
+            if (out_f32) {
               float* o = reinterpret_cast<float*>(p.out) + split * p.split_stride + row * p.ldd + col0;
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -479,7 +480,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (gtid == 0) tma_store_wait_read_n(NB - 1);
             named_bar_sync(bar_id, 128);
           }
-          if (p.out_f32) {
+          if (out_f32) {
             // one 128 B (32 x fp32) slice per TMA store
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -496,7 +497,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (s_end) {
             fence_proxy_async_smem();
             named_bar_sync(bar_id, 128);
-            const int scol = p.out_f32 ? col0 : col0 - 32;
+            const int scol = out_f32 ? col0 : col0 - 32;
             if (gtid == 0) {
               if (scol < p.N) {
                 asm volatile(
@@ -524,17 +525,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const int wq = gtid >> 5;
               const int piece = lane & 3;
               const int chunk = wq * 2 + (piece >> 1);
+              const int r0 = lane >> 2;        // row of load i is i*8 + r0: its swizzle phase (row & 7) is r0 for every i
+              const uint8_t* const sp = sbuf + r0 * 128 + ((chunk ^ r0) << 4) + (piece & 1) * 8;
               float sx[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+#pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const int r = i * 8 + (lane >> 2);
-                const uint2 w2 = *reinterpret_cast<const uint2*>(sbuf + r * 128 + ((chunk ^ (r & 7)) << 4) + (piece & 1) * 8);
-                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w2.x));
-                const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w2.y));
-                sx[0] += a.x; sq[0] += a.x * a.x;
-                sx[1] += a.y; sq[1] += a.y * a.y;
-                sx[2] += b.x; sq[2] += b.x * b.x;
-                sx[3] += b.y; sq[3] += b.y * b.y;
+                const uint2 w2 = *reinterpret_cast<const uint2*>(sp + i * 1024);
+                const float a0 = __uint_as_float(w2.x << 16), a1 = __uint_as_float(w2.x & 0xffff0000u);
+                const float b0 = __uint_as_float(w2.y << 16), b1 = __uint_as_float(w2.y & 0xffff0000u);
+                sx[0] += a0; sq[0] = fmaf(a0, a0, sq[0]);
+                sx[1] += a1; sq[1] = fmaf(a1, a1, sq[1]);
+                sx[2] += b0; sq[2] = fmaf(b0, b0, sq[2]);
+                sx[3] += b1; sq[3] = fmaf(b1, b1, sq[3]);
               }
 #pragma unroll
               for (int o = 4; o < 32; o <<= 1) {

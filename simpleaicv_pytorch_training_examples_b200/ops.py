@@ -147,6 +147,20 @@ def cast_bf16(src, out=None):
     return out
 
 
+def u8_normalize(images, mean, std, out=None):
+    """images: uint8 [N, H, W, 3] (device) -> fp32 [N, 3, H, W] = (x / 255 - mean[c]) / std[c]: ToTensor + Normalize +
+    the collater's permute of the reference (classification/common.py:228-248,645-665) on the device, bit-identical."""
+    import ctypes
+    assert images.is_cuda and images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3 and images.is_contiguous()
+    n, h, w, _ = images.shape
+    if out is None:
+        out = torch.empty(n, 3, h, w, device=images.device, dtype=torch.float32)
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _lib.call('saicv_u8_nhwc_to_nchw_norm', _p(images), _p(out), n, h, w, m3, s3, _stream())
+    return out
+
+
 def nchw_to_nhwc_bf16(x, out=None):
     n, c, h, w = x.shape
     if out is None:

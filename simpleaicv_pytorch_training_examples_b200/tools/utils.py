@@ -204,8 +204,11 @@ class CudaPrefetcher:
     batch.  Consequently a yielded batch is valid until the consumer requests the next one (work already
     enqueued on the consumer's stream still sees the old contents; tensors to keep longer must be cloned)."""
 
-    def __init__(self, loader, device=None, copy_streams=4):
-        """copy_streams > 1: tensors of 32 MB and more are copied in that many chunks on separate streams.  Measured on the
+    def __init__(self, loader, device=None, copy_streams=4, normalize=None):
+        """normalize=(mean, std): batches whose 'image' is a uint8 [B, H, W, 3] tensor (classification.common.
+        Uint8ClassificationCollater) are copied as uint8 - a quarter of the bytes - and turned into the fp32 NCHW
+        normalised batch on the device, on the copy stream (csrc/capi_input.cu).
+        copy_streams > 1: tensors of 32 MB and more are copied in that many chunks on separate streams.  Measured on the
         B200 boxes of this pool (tests/profile_h2d.py, profiles/r02_h2d_prefetch.md): a single copy stream moves the 154 MB
         ResNet-50 batch at 34 GB/s on an idle GPU but at ~6 GB/s while kernels are running (25 ms, longer than the 27 ms
         step hides), two or more streams keep 45 - 55 GB/s under load; end to end 7.3 k -> 9.4 k img/s with four."""
@@ -215,6 +218,7 @@ class CudaPrefetcher:
         self._extra = [torch.cuda.Stream(self.device) for _ in range(max(0, int(copy_streams) - 1))]
         self._slots = [{}, {}]
         self._free = [None, None]      # event after which slot k may be overwritten
+        self.normalize = normalize
 
     def __len__(self):
         return len(self.loader)
@@ -249,6 +253,13 @@ class CudaPrefetcher:
                 out[name] = buf
             for st in self._extra:
                 self.stream.wait_stream(st)
+            img = out.get('image')
+            if self.normalize is not None and torch.is_tensor(img) and img.dtype == torch.uint8:
+                from .. import ops
+                nb = slot.get('image_f32')
+                if nb is None or nb.shape[0] != img.shape[0] or nb.shape[2:] != img.shape[1:3]:
+                    nb = slot['image_f32'] = torch.empty(img.shape[0], 3, img.shape[1], img.shape[2], device=self.device)
+                out['image'] = ops.u8_normalize(img, self.normalize[0], self.normalize[1], out=nb)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         return out, ev

@@ -78,7 +78,8 @@ def test_fused_step_matches_torch(kind, unaligned):
     ref2.load_state_dict(sd)
     key = 'exp_avg' if kind == 'adamw' else 'momentum_buffer'
     for p, q in zip(pa, pb):
-        assert torch.allclose(ref.state[p][key], mine.state[q][key], rtol=1e-5, atol=1e-7)
+        a, b = ref.state[p][key], mine.state[q][key]
+        assert (a - b).abs().max().item() <= 4e-6 * a.abs().max().item() + 1e-7
         assert torch.equal(ref2.state[p][key], mine.state[q][key])
     if kind == 'adamw':
         assert float(ref2.state[pa[0]]['step']) == 12.
