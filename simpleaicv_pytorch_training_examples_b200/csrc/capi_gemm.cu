@@ -134,17 +134,21 @@ void tune_override(int* bn, int* stages, int* nb) {
   if (nb && c > 0) *nb = c;
 }
 
-// Split of the 227 KB between the operand ring (stages) and the epilogue staging slices (nb per half).
-// A tile whose reduction is >= 4 k-blocks long keeps the tensor pipe busy for > 1 us, which hides a
-// serialised epilogue: it gets >= 4 ring stages and whatever is left for the slices.  Short reductions
-// (the 1x1 convolutions of layers 1-3, K = 64..256) are epilogue / HBM bound: 3 stages are enough
-// to keep the loads of the following tiles in flight and the rest goes to 2-3 slices per half.
+// Split of the 227 KB between the operand ring (stages) and the epilogue staging slices (nb per half), from the sweep
+// of tests/profile_gemm_tune.py on a B200 (profiles/r02_gemm_epilogue_ncu.md):
+//  * no aux operand: two slices per half whenever >= 3 stages remain (>= 4 for reductions of 4+ k-blocks) - a TMA store
+//    is then never waited for right after it was issued (conv 1x1 c64->k256 56x56: 118 -> 96 us);
+//  * aux operand by TMA: the slices are also the landing buffers of the next aux tiles, so depth matters more than ring
+//    stages while the reduction is short: <= 4 k-blocks -> 3 slices / 2+ stages (c256->k64 dgrad + shortcut: 257 -> 203 us),
+//    fp32 tiles (8 slices per 128 x 256 tile) of <= 16 k-blocks -> 2 slices / 3 stages (ViT proj + fp32 residual: 96 -> 92 us);
+//    everything longer keeps 4 stages first (ViT fc2 data gradient with dGELU: 328 us at 4 / 1, 346 us at 3 / 2).
 template <int BN>
 void pick_smem_split(const GemmParams& p, int stat_bytes, int* stages_out, int* nb_out) {
   using Cfg = GemmCfg<BN>;
   const int budget = kSmemBudget - stat_bytes;
   const bool has_aux = p.aux_tma != 0;
-  const int min_stages = p.kb_per_split >= 4 ? 4 : 3;
+  const int kb = p.kb_per_split;
+  const int min_stages = has_aux ? (kb <= 4 ? 2 : (kb <= 16 && p.out_f32) ? 3 : 4) : (kb >= 4 ? 4 : 3);
   int nb = has_aux ? 3 : 2;
   while (nb > 1 && (budget - 2 * nb * kStoreBufBytes) / Cfg::kStageBytes < min_stages) --nb;
   int stages = (budget - 2 * nb * kStoreBufBytes) / Cfg::kStageBytes;

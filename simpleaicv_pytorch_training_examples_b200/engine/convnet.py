@@ -301,13 +301,17 @@ class ResidualBlockRT:
             shortcut = self.down.conv_bwd(dyd, td, sink)
             if isinstance(shortcut, tuple):
                 strided, shortcut = shortcut[1], None
-        dx = last.conv_bwd(dy, tl, sink)
-        for u, t in zip(reversed(self.units[:-1]), reversed(tapes[:-1])):
+        # The shortcut gradient joins the main path inside the data-gradient GEMM of the block's FIRST conv: its tile is
+        # the aux operand of that launch's epilogue (TMA-loaded into the staging slice, gemm_sm100.cuh aux_tma), which
+        # replaces a separate read-read-write pass over the block input (add_bf16: 13 launches, 1.06 ms per ResNet-50 step).
+        first_unit = self.units[0]
+        fuse = shortcut is not None and not (first_unit.stride == 2 and first_unit.r == 1)   # that case returns a compact gradient
+        n_main = len(self.units) - 1
+        dx = last.conv_bwd(dy, tl, sink, add=shortcut if (fuse and n_main == 0) else None)
+        for i, (u, t) in enumerate(zip(reversed(self.units[:-1]), reversed(tapes[:-1]))):
             dy, _ = u.bn_bwd(dx, t, sink)
-            dx = u.conv_bwd(dy, t, sink)
-        # TODO(perf): fuse this add into the dgrad epilogue once the epilogue loads its residual
-        # tile with TMA (the per-thread row-strided loads of EPI_RESID_BF16 are slower than this pass)
-        if shortcut is not None:
+            dx = u.conv_bwd(dy, t, sink, add=shortcut if (fuse and i == n_main - 1) else None)
+        if shortcut is not None and not fuse:
             ops.add_bf16(dx, shortcut)
         if strided is not None:
             ops.add_strided2(dx, strided)
@@ -351,8 +355,7 @@ class DarkBlockRT:
         dy, _ = self.u2.bn_bwd(dout, t2, sink)          # mask of u2's own activation, recomputed from y
         dx = self.u2.conv_bwd(dy, t2, sink)
         dy, _ = self.u1.bn_bwd(dx, t1, sink)
-        dx = self.u1.conv_bwd(dy, t1, sink)
-        return ops.add_bf16(dx, dout)
+        return self.u1.conv_bwd(dy, t1, sink, add=dout)   # 1x1 stride-1 conv: the shortcut gradient is the epilogue's aux operand
 
 
 class MaxPoolRT:
