@@ -410,6 +410,19 @@ int saicv_multi_tensor_clip_coef(const void* tensors, const int* chunk_tensor, c
 int saicv_u8_nhwc_to_nchw_norm(const void* in, float* out, int n, int h, int w, const float* mean3, const float* std3,
                                void* stream);
 
+/* ---- token gather / scatter for masked-token models (csrc/capi_tokens.cu) -----------------------------
+ * out fp32 [b][r][c] = (idx[b][r] >= 0 ? src[b][idx[b][r]][:] : fill[:]) + (pos ? pos[pos_idx ? pos_idx[b][r] : r][:] : 0);
+ * src fp32 [b][src_rows][c].  One call is the torch.gather + cat(cls / mask token) + position-encoding add of
+ * masked_image_modeling/models/vit_mae.py:171-186 (encoder: keep the visible patches) and :339-354 (decoder: un-shuffle).
+ * Backward: dsrc[b][idx][:] = dout[b][r][:] for idx >= 0 (fp32 or bf16; rows never referenced must be pre-zeroed by the
+ * caller) and fill_partial[slab][c] = sum of the dout rows with idx < 0 (saicv_token_fill_slabs(b * r) slabs, to be folded
+ * with saicv_reduce_partials: the gradient of the cls / mask token).  Either output may be NULL.  c %% 4 == 0. */
+int saicv_token_gather_fwd(const float* src, long long src_rows, const int* idx, const float* fill, const float* pos,
+                           const int* pos_idx, float* out, int b, int r, int c, void* stream);
+int saicv_token_fill_slabs(long long rows);
+int saicv_token_gather_bwd(const float* dout, const int* idx, void* dsrc, int dsrc_bf16, long long src_rows,
+                           float* fill_partial, int b, int r, int c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -320,6 +320,36 @@ def colsum(x, out, accumulate=False):
     return out
 
 
+# ----------------------------------------------------------------------------- masked-token models
+def token_gather_fwd(src, idx, fill, pos=None, pos_idx=None, out=None):
+    """src fp32 [B, S, C], idx int32 [B, R] (-1 = take `fill` [C]), pos fp32 [P, C] added by row (pos_idx int32 [B, R] or the
+    row number): out fp32 [B, R, C] (csrc/capi_tokens.cu)."""
+    b, s_rows, c = src.shape
+    r = idx.shape[1]
+    assert src.dtype == torch.float32 and idx.dtype == torch.int32 and idx.shape[0] == b and src.is_contiguous() and idx.is_contiguous()
+    if out is None:
+        out = torch.empty(b, r, c, device=src.device, dtype=torch.float32)
+    _lib.call('saicv_token_gather_fwd', _p(src), s_rows, _p(idx), _p(fill), _p(pos), _p(pos_idx), _p(out), b, r, c, _stream())
+    return out
+
+
+def token_gather_bwd(dout, idx, src_rows, dsrc_dtype=torch.bfloat16, want_fill=True, zero=True):
+    """dout fp32 [B, R, C] -> (dsrc [B, src_rows, C] in `dsrc_dtype`, dfill fp32 [C] or None).  zero: some source rows are
+    not referenced by idx (their gradient is 0) - pre-zero dsrc."""
+    b, r, c = dout.shape
+    assert dout.dtype == torch.float32 and dout.is_contiguous() and dsrc_dtype in (torch.bfloat16, torch.float32)
+    dsrc = (torch.zeros if zero else torch.empty)(b, src_rows, c, device=dout.device, dtype=dsrc_dtype)
+    part = dfill = None
+    if want_fill:
+        nslab = _lib.load().saicv_token_fill_slabs(b * r)
+        part = torch.empty(nslab, c, device=dout.device, dtype=torch.float32)
+    _lib.call('saicv_token_gather_bwd', _p(dout), _p(idx), _p(dsrc), int(dsrc_dtype == torch.bfloat16), src_rows, _p(part), b, r, c, _stream())
+    if want_fill:
+        dfill = torch.empty(c, device=dout.device, dtype=torch.float32)
+        reduce_partials(part, dfill)
+    return dsrc, dfill
+
+
 # ----------------------------------------------------------------------------- ViT blocks
 def layernorm_fwd(x, gamma, beta, eps, out=None, stats=None):
     rows, c = x.numel() // x.shape[-1], x.shape[-1]
