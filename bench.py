@@ -31,16 +31,21 @@ import torch.distributed as dist  # noqa: E402
 METRICS = {'resnet50': 'images/sec (ResNet-50 224x224 training step, whole job)',
            'vit_base_patch16': 'images/sec (ViT-B/16 224x224 training step, whole job)',
            'sam_h_encoder': 'images/sec (SAM ViT-H image encoder 1024x1024 training step, whole job)',
-           'resnet50_detr': 'images/sec (DETR-R50 1024x1024 training step, whole job)'}
+           'resnet50_detr': 'images/sec (DETR-R50 1024x1024 training step, whole job)',
+           'vit_base_mae': 'images/sec (MAE ViT-B/16 224x224 pre-training step, whole job)'}
 WORKLOADS = {'resnet50': 'ResNet-50 224x224 bs256/GPU training step (fwd+CELoss+bwd+grad all-reduce+SGD)',
              'vit_base_patch16': 'ViT-B/16 224x224 bs256/GPU training step (fwd+OneHotLabelCELoss+bwd+grad all-reduce+AdamW)',
              'sam_h_encoder': ('SAM ViT-H image encoder 1024x1024 bs8/GPU training step (encoder fwd + feature MSE against a synthetic '
                                'teacher map, the train_distill_sam_encoder step body + bwd + grad all-reduce + AdamW); prompt encoder / '
                                'mask decoder are outside the built path'),
              'resnet50_detr': ('DETR-R50 1024x1024 bs4/GPU training step (the shipped res50_detr_yoloresize1024 shape; fwd + DETRLoss with the '
-                               'Hungarian matcher on the host + bwd + grad all-reduce + AdamW; dropout 0.1 as in the reference constructor)')}
-FWD_FLOPS = {'resnet50': 8.178e9, 'vit_base_patch16': 35.13e9, 'sam_h_encoder': 5961e9, 'resnet50_detr': 191.6e9}   # per image forward; a step is 3x
-ALGO_BYTES = {'resnet50': 130e6, 'vit_base_patch16': 3 * 65e6, 'sam_h_encoder': 3 * 3.1e9, 'resnet50_detr': 130e6 * 20.9}  # per image per step, activations once each way (8d)
+                               'Hungarian matcher on the host + bwd + grad all-reduce + AdamW; dropout 0.1 as in the reference constructor)'),
+             'vit_base_mae': ('MAE pre-training, vit_base_patch16_224_mae_pretrain_model 224x224 bs256/GPU (75 % of the patches masked: encoder on '
+                              '50 tokens, 8-block 512-wide decoder on 197; fwd + MSELoss on removed patches + bwd + grad all-reduce + AdamW)')}
+FWD_FLOPS = {'resnet50': 8.178e9, 'vit_base_patch16': 35.13e9, 'sam_h_encoder': 5961e9, 'resnet50_detr': 191.6e9,
+             'vit_base_mae': 19.6e9}   # MAE: from the layer shapes (encoder 50 tokens x 12 blocks, decoder 197 tokens x 8 blocks)
+FWD_FLOPS_NOTE = 'per image forward (SURVEY.md 8d); a step is 3x'
+ALGO_BYTES = {'resnet50': 130e6, 'vit_base_patch16': 3 * 65e6, 'sam_h_encoder': 3 * 3.1e9, 'resnet50_detr': 130e6 * 20.9, 'vit_base_mae': 3 * 40e6}  # per image per step, activations once each way (8d)
 
 
 def _peaks():
@@ -130,6 +135,9 @@ def synthetic_batch(model_name, B, rank, pin):
         y = torch.randn(B, 256, 64, 64, generator=g)
         return (x.pin_memory(), y.pin_memory()) if pin else (x, y)
     x = torch.randn(B, 3, 224, 224, generator=g)
+    if model_name == 'vit_base_mae':   # label = the patchified image (MAESelfSupervisedPretrainCollater's tensors)
+        y = torch.einsum('nchpwq->nhwpqc', x.reshape(B, 3, 14, 16, 14, 16)).reshape(B, 196, 768).contiguous()
+        return (x.pin_memory(), y.pin_memory()) if pin else (x, y)
     if model_name == 'resnet50':
         y = torch.randint(0, 1000, (B,), generator=g)
     else:  # mixup-style soft labels
@@ -441,6 +449,18 @@ def measure_model(model_name, args, rank, world, local_rank, dump_path=None, wit
             optimizer = ('AdamW', {'lr': 1e-4, 'global_weight_decay': False, 'weight_decay': 0.05,
                                    'no_weight_decay_layer_name_list': [], 'capturable': world == 1 or not args.no_graph_ddp})
         opt, _ = tutils.build_optimizer(_Cfg, model)
+    elif model_name == 'vit_base_mae':
+        from simpleaicv_pytorch_training_examples_b200.masked_image_modeling import losses as mim_losses
+        from simpleaicv_pytorch_training_examples_b200.masked_image_modeling.models import vit_mae
+        model = vit_mae.vit_base_patch16_224_mae_pretrain_model().to(dev).train()
+        mse = mim_losses.MSELoss().to(dev)
+
+        def crit(outs, y):
+            return mse(outs[0], y, outs[1])
+
+        class _Cfg:
+            optimizer = ('AdamW', {'lr': 1.5e-4, 'global_weight_decay': False, 'weight_decay': 0.05, 'no_weight_decay_layer_name_list': []})
+        opt, _ = tutils.build_optimizer(_Cfg, model)
     elif model_name == 'resnet50':
         model = backbones.resnet50(num_classes=1000).to(dev).train()
         crit = losses.CELoss().to(dev)
@@ -627,6 +647,10 @@ def run_b200(args, rank, world, local_rank):
         second = 'vit_base_patch16' if args.model == 'resnet50' else 'resnet50'
         other = measure_model(second, args, rank, world, local_rank,
                               args.dump_ops.replace('.csv', f'_{second}.csv') if args.dump_ops else None)
+    mae_rec = None
+    if args.mae:
+        mae_rec = measure_model('vit_base_mae', args, rank, world, local_rank,
+                                args.dump_ops.replace('.csv', '_vit_base_mae.csv') if args.dump_ops else None)
     sam_rec = None
     if args.sam:
         sam_rec = measure_model('sam_h_encoder', args, rank, world, local_rank,
@@ -662,6 +686,9 @@ def run_b200(args, rank, world, local_rank):
         name = 'vit_base_patch16' if args.model == 'resnet50' else 'resnet50'
         line[name] = {k: other[k] for k in SUB}
         line[name]['images_per_sec_per_gpu'] = other['value'] / world
+    if mae_rec is not None:
+        line['vit_base_mae'] = {k: mae_rec[k] for k in SUB}
+        line['vit_base_mae']['images_per_sec_per_gpu'] = mae_rec['value'] / world
     if sam_rec is not None:
         line['sam_h_encoder'] = {k: sam_rec[k] for k in SUB}
         line['sam_h_encoder']['images_per_sec_per_gpu'] = sam_rec['value'] / world
@@ -688,6 +715,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-second-model', action='store_true', help='skip the sub-record of the other BASELINE model')
     ap.add_argument('--detr', action='store_true', help='add the DETR-R50 sub-record (BASELINE configs[4]; shipped 1024x1024 shape, bs4)')
+    ap.add_argument('--mae', action='store_true', help='add the MAE ViT-B/16 pre-training sub-record (SURVEY.md 8 f4)')
     ap.add_argument('--sam', action='store_true', help='add the SAM ViT-H image-encoder sub-record (BASELINE configs[3]: bs8, 1024x1024)')
     ap.add_argument('--no-graph-ddp', action='store_true',
                     help='N > 1: launch the step eagerly instead of capturing it (NCCL bucket all-reduces included) in one CUDA graph')

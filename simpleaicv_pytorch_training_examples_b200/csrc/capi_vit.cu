@@ -283,9 +283,11 @@ int saicv_layernorm_fwd(const float* x, const float* gamma, const float* beta, v
     case 768: ln_fwd_kernel<6><<<grid, 256, 0, ST>>>(x, gamma, beta, yy, stats, rows, eps); break;
     case 1024: ln_fwd_kernel<8><<<grid, 256, 0, ST>>>(x, gamma, beta, yy, stats, rows, eps); break;
     case 1280: ln_fwd_kernel<10><<<grid, 256, 0, ST>>>(x, gamma, beta, yy, stats, rows, eps); break;
+    case 512: ln_fwd_kernel<4><<<grid, 256, 0, ST>>>(x, gamma, beta, yy, stats, rows, eps); break;
+    case 384: ln_fwd_kernel<3><<<grid, 256, 0, ST>>>(x, gamma, beta, yy, stats, rows, eps); break;
     case 256: ln_fwd_kernel<2><<<grid, 256, 0, ST>>>(x, gamma, beta, yy, stats, rows, eps); break;
     case 128: ln_fwd_kernel<1><<<grid, 256, 0, ST>>>(x, gamma, beta, yy, stats, rows, eps); break;
-    default: return set_error("saicv_layernorm_fwd: unsupported width %d (128, 256, 768, 1024, 1280)", c);
+    default: return set_error("saicv_layernorm_fwd: unsupported width %d (128, 256, 384, 512, 768, 1024, 1280)", c);
   }
   return check_launch("ln_fwd_kernel");
 }
@@ -302,6 +304,8 @@ int saicv_layernorm_bwd(const void* dy, const float* x, const float* gamma, cons
     case 768: ln_bwd_kernel<6><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
     case 1024: ln_bwd_kernel<8><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
     case 1280: ln_bwd_kernel<10><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
+    case 512: ln_bwd_kernel<4><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
+    case 384: ln_bwd_kernel<3><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
     case 256: ln_bwd_kernel<2><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
     case 128: ln_bwd_kernel<1><<<grid, 256, 0, ST>>>(d, x, gamma, stats, dres, dx, xb, bf16_row_scale, rows_per_scale, partials, rows); break;
     default: return set_error("saicv_layernorm_bwd: unsupported width %d", c);

@@ -1,5 +1,5 @@
 """train / test loops of the classification task with the call signatures of the reference's
-tools/scripts.py:36-113 (test_classification) and :116-275 (train_classification).
+tools/scripts.py:36-113 (test_classification), :116-275 (train_classification) and :1774-1934 (train_mae_self_supervised_learning).
 
 Arithmetic per step is the reference's: forward, criterion, backward (gradient average across
 ranks), optional clipping, optimizer step, per-iteration LR.  Control flow is tightened for a
@@ -28,7 +28,9 @@ def _is_master(config):
     return config.local_rank == 0 and getattr(config, 'total_rank', 0) == 0
 
 
-def train_classification(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config):
+def train_classification(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config, compute_loss=None):
+    """compute_loss(model, criterion, images, labels) -> loss overrides the default criterion(model(images), labels): the
+    epoch bodies of the reference that differ only there (train_mae_self_supervised_learning) share this loop."""
     losses = AverageMeter()
     model.train()
     accum = config.accumulation_steps
@@ -43,8 +45,11 @@ def train_classification(train_loader, model, criterion, optimizer, scheduler, e
         bad = (~torch.isfinite(images)).any()
         if labels.dtype.is_floating_point:
             bad = bad | (~torch.isfinite(labels)).any()
-        outputs = model(images)
-        loss = criterion(outputs, labels)
+        if compute_loss is not None:
+            loss = compute_loss(model, criterion, images, labels)
+        else:
+            outputs = model(images)
+            loss = criterion(outputs, labels)
         bad = bad | (~torch.isfinite(loss)) | (loss == 0.)
         loss = loss / accum
         sync_step = iter_index % accum == 0
@@ -85,6 +90,15 @@ def train_classification(train_loader, model, criterion, optimizer, scheduler, e
                         f'lr: {scheduler.current_lr:.6f}, loss: {loss_sum / world * accum:.4f}')
         iter_index += 1
     return losses.avg * accum
+
+
+def train_mae_self_supervised_learning(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config):
+    """tools/scripts.py:1774-1934 of the reference: `outputs, masks = model(images); loss = criterion(outputs, labels, masks)`
+    with the guards / accumulation / clipping / per-iteration LR of train_classification (labels = patchified images)."""
+    def mae_loss(model, criterion, images, labels):
+        outputs, masks = model(images)
+        return criterion(outputs, labels, masks)
+    return train_classification(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config, compute_loss=mae_loss)
 
 
 def train_epoch_with_loss_terms(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config, compute,
