@@ -6,6 +6,21 @@ import numpy as np
 import torch
 
 
+def load_state_dict(saved_model_path, model, excluded_layer_name=()):
+    """classification/common.py:758-800 of the reference: loads the entries of a saved ``state_dict`` file whose name and
+    shape match ``model`` (and whose name contains none of ``excluded_layer_name``); an empty path is a no-op."""
+    if not saved_model_path:
+        return
+    saved = torch.load(saved_model_path, map_location=torch.device('cpu'), weights_only=True)
+    own = model.state_dict()
+    keep = {n: w for n, w in saved.items()
+            if n in own and w.shape == own[n].shape and not any(e in n for e in excluded_layer_name)}
+    skipped = [n for n in saved if n not in keep]
+    if skipped:
+        print(f'not loaded: {len(skipped)} of {len(saved)} saved tensors (name / shape mismatch or excluded)')
+    model.load_state_dict(keep, strict=False)
+
+
 class Uint8ClassificationCollater:
     """Counterpart of ClassificationCollater (common.py:645-665) for samples whose 'image' is still the decoder's uint8
     [H, W, 3] array (i.e. the transform list ends BEFORE TorchMeanStdNormalize / Normalize): stacks into ONE pinned uint8

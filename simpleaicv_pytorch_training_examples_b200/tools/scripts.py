@@ -169,6 +169,32 @@ def train_epoch_with_loss_terms(train_loader, model, criterion, optimizer, sched
     return losses.avg * accum
 
 
+def train_distill_classification(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config):
+    """tools/scripts.py:291-500 of the reference: `tea_outputs, stu_outputs = model(images)`; `criterion` is a dict of
+    losses, CELoss / OneHotLabelCELoss apply to the student (and to the teacher when it is not frozen), every other entry
+    to (student, teacher); each term is weighted by config.loss_ratio[name]; the frozen teacher stays in eval mode."""
+    model.train()
+    if config.freeze_teacher:
+        (model.module if hasattr(model, 'module') else model).teacher.eval()
+
+    def compute(data):
+        images, labels = data['image'], data['label']
+        tea_outputs, stu_outputs = model(images)
+        loss_value = {}
+        for name, fn in criterion.items():
+            if name in ('CELoss', 'OneHotLabelCELoss'):
+                if not config.freeze_teacher:
+                    loss_value['tea_' + name] = fn(tea_outputs, labels) * config.loss_ratio[name]
+                loss_value['stu_' + name] = fn(stu_outputs, labels) * config.loss_ratio[name]
+            else:
+                loss_value[name] = fn(stu_outputs, tea_outputs) * config.loss_ratio[name]
+        checked = (images, labels) if labels.dtype.is_floating_point else (images,)
+        return loss_value, checked, images.size(0)
+
+    return train_epoch_with_loss_terms(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config, compute,
+                                       total_name='loss')
+
+
 def train_detection(train_loader, model, criterion, optimizer, scheduler, epoch, logger, config):
     """One epoch of detection training with the reference's step semantics (tools/scripts.py:900-1092): DETR batches carry
     'image', 'scaled_annots' and 'mask'; the criterion returns a dict of loss terms whose sum is differentiated."""
