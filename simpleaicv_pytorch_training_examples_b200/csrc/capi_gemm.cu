@@ -181,7 +181,7 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, con
   if (stages < 2) return set_error("gemm_sm100_kernel<%d>: %d bytes of statistics do not fit in shared memory", BN, stat_bytes);
   const_cast<GemmParams&>(p).num_stages = stages;
   const_cast<GemmParams&>(p).store_bufs = nb;
-  gemm_sm100_kernel<BN, VAR><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a, b, d, r, p);
+  gemm_sm100_kernel<BN, VAR><<<grid, GemmVariant<VAR>::kThreads, Cfg::kSmemBytes, st>>>(a, b, d, r, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm_sm100_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
   count_launch(1);
@@ -218,12 +218,14 @@ int dispatch(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorM
   int var = VAR_FULL;
   if (!getenv("SAICV_GEMM_FULL_VARIANT")) {
     if (p.aux_tma && !(p.epi_flags & ~GemmVariant<VAR_AUX>::kMask)) var = VAR_AUX;
-    else if (!p.aux_tma && !p.out_f32 && !(p.epi_flags & ~GemmVariant<VAR_PLAIN_BF16>::kMask)) var = VAR_PLAIN_BF16;
+    else if (!p.aux_tma && !p.out_f32 && !(p.epi_flags & ~GemmVariant<VAR_PLAIN_BF16>::kMask))
+      var = ((p.epi_flags & EPI_STATS) && !getenv("SAICV_GEMM_INLINE_STATS")) ? VAR_STATS_BF16 : VAR_PLAIN_BF16;
     else if (!p.aux_tma && p.out_f32 && !(p.epi_flags & ~GemmVariant<VAR_PLAIN_F32>::kMask)) var = VAR_PLAIN_F32;
   }
 #define SAICV_LAUNCH_BN(BN_)                                                         \
   switch (var) {                                                                     \
     case VAR_PLAIN_BF16: return launch<BN_, VAR_PLAIN_BF16>(a, b, d, r, p, st);      \
+    case VAR_STATS_BF16: return launch<BN_, VAR_STATS_BF16>(a, b, d, r, p, st);      \
     case VAR_PLAIN_F32: return launch<BN_, VAR_PLAIN_F32>(a, b, d, r, p, st);        \
     case VAR_AUX: return launch<BN_, VAR_AUX>(a, b, d, r, p, st);                    \
     default: return launch<BN_, VAR_FULL>(a, b, d, r, p, st);                        \

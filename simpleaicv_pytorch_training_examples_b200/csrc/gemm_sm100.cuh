@@ -96,19 +96,25 @@ struct GemmParams {
 //   VAR_PLAIN_BF16  bf16 output, optional bias / ReLU / BatchNorm statistics       (conv fprop, plain dgrad, Linear)
 //   VAR_PLAIN_F32   fp32 output, optional bias                                       (split-K weight gradients, fp32 Linear)
 //   VAR_AUX         aux operand by TMA (fp32 residual, bf16 addend / ReLU mask / GELU pre-activation), bias, row scale
-enum : int { VAR_FULL = 0, VAR_PLAIN_BF16 = 1, VAR_PLAIN_F32 = 2, VAR_AUX = 3 };
+//   VAR_STATS_BF16  VAR_PLAIN_BF16 with the BatchNorm statistics taken by FOUR EXTRA WARPS (512 threads): the column sums of
+//                   a staged slice cost ~2.8x the work of staging it; done by the 8 epilogue warps they put +90 us on a
+//                   96 us conv (c64->k256 56x56).  The stats warps read the slice from shared memory while the epilogue
+//                   warps are already draining the next chunk (handshake: staged / stats-done mbarriers per slice).
+enum : int { VAR_FULL = 0, VAR_PLAIN_BF16 = 1, VAR_PLAIN_F32 = 2, VAR_AUX = 3, VAR_STATS_BF16 = 4 };
 template <int VAR>
 struct GemmVariant {
   static constexpr int kMask = VAR == VAR_FULL ? 0x7fffffff
-                               : VAR == VAR_PLAIN_BF16 ? (EPI_BIAS | EPI_RELU | EPI_STATS)
+                               : (VAR == VAR_PLAIN_BF16 || VAR == VAR_STATS_BF16) ? (EPI_BIAS | EPI_RELU | EPI_STATS)
                                : VAR == VAR_PLAIN_F32 ? EPI_BIAS
                                : (EPI_BIAS | EPI_ROW_SCALE | EPI_RESID | EPI_RESID_BF16 | EPI_MUL_DGELU | EPI_MUL_DRELU);
-  static constexpr int kOut = VAR == VAR_PLAIN_BF16 ? 1 : VAR == VAR_PLAIN_F32 ? 2 : 0;   // 0: run time, 1: bf16, 2: fp32
+  static constexpr int kOut = (VAR == VAR_PLAIN_BF16 || VAR == VAR_STATS_BF16) ? 1 : VAR == VAR_PLAIN_F32 ? 2 : 0;   // 0: run time, 1: bf16, 2: fp32
   static constexpr int kAux = VAR == VAR_FULL ? 0 : VAR == VAR_AUX ? 2 : 1;                // 0: run time, 1: never, 2: always by TMA
+  static constexpr bool kStatsWarps = VAR == VAR_STATS_BF16;                               // statistics by warps 12..15
+  static constexpr int kThreads = kStatsWarps ? kGemmThreads + 128 : kGemmThreads;
 };
 
 template <int BN, int VAR>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(GemmVariant<VAR>::kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                   const GemmParams p) {
@@ -135,7 +141,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* aux_bar = tempty_bar + 2;   // [2 halves][kMaxStoreBufs]: aux slice landed in staging slice b
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * kMaxStoreBufs);
+  uint64_t* staged_bar = aux_bar + 2 * kMaxStoreBufs;    // [2][kMaxStoreBufs] VAR_STATS_BF16: slice b of the half is staged
+  uint64_t* sdone_bar = staged_bar + 2 * kMaxStoreBufs;  // [2][kMaxStoreBufs] the four stats warps have read slice b
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdone_bar + 2 * kMaxStoreBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -155,7 +163,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);
     }
-    for (int i = 0; i < 2 * kMaxStoreBufs; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < 2 * kMaxStoreBufs; ++i) {
+      mbar_init(&aux_bar[i], 1);
+      mbar_init(&staged_bar[i], 1);
+      mbar_init(&sdone_bar[i], 4);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -290,7 +302,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ================================================================ epilogue
     // 8 warps: warp e handles TMEM sub-partition (lanes) e%4 and column half e/4 of every tile, so
     // two warps drain each 32-lane quadrant concurrently.  Each half owns NB 16 KB staging slices
@@ -337,9 +349,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int la = NB > 1 ? NB - 1 : 1;
       for (int i = 0; i < la; ++i) request_aux();
     }
+    constexpr int kStatBarThreads = V::kStatsWarps ? 384 : 256;
+    uint32_t sd_phase = 0;     // VAR_STATS_BF16: bit b = parity of the stats-done barrier of staging slice b
     if (do_stats) {
       for (int j = threadIdx.x - 128; j < 2 * p.N; j += 256) sStat[j] = 0.f;
-      named_bar_sync(3, 256);
+      named_bar_sync(3, kStatBarThreads);
     }
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int n_blk = w % num_n;
@@ -476,8 +490,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         } else {
           if (s_begin && !aux_tma) {
-            // the store that last read this staging slice (NB slices ago) must have drained it
-            if (gtid == 0) tma_store_wait_read_n(NB - 1);
+            // the store that last read this staging slice (NB slices ago) must have drained it (and the stats warps too)
+            if (gtid == 0) {
+              tma_store_wait_read_n(NB - 1);
+              if (V::kStatsWarps && do_stats) {
+                mbar_wait(&sdone_bar[half * kMaxStoreBufs + bufi], ((sd_phase >> bufi) & 1u) ^ 1u);
+                sd_phase ^= (1u << bufi);
+              }
+            }
             named_bar_sync(bar_id, 128);
           }
           if (out_f32) {
@@ -513,7 +533,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 request_aux();
               }
             }
-            if (do_stats) {
+            if (V::kStatsWarps && do_stats) {
+              if (gtid == 0) mbar_arrive(&staged_bar[half * kMaxStoreBufs + bufi]);   // hand the slice to the stats warps
+            } else if (do_stats) {
               // BatchNorm statistics of the slice just staged (the bf16 values as stored), read back
               // from the swizzled buffer (conflict free: a warp reads the 128 contiguous bytes of one
               // row) concurrently with the TMA store of the same buffer.  Rows >= M / cols >= N are zero.
@@ -564,9 +586,73 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (gtid == 0) tma_store_wait<0>();
     if (do_stats) {
-      named_bar_sync(3, 256);
+      named_bar_sync(3, kStatBarThreads);
       float* dst = p.stats_partial + (long long)blockIdx.x * 2 * p.N;
       for (int j = threadIdx.x - 128; j < 2 * p.N; j += 256) dst[j] = sStat[j];
+    }
+  } else if (V::kStatsWarps && warp >= 12) {
+    // ================================================================ statistics warps (VAR_STATS_BF16)
+    // Warp wq owns columns wq*16 .. +15 of every staged 64-column slice of BOTH epilogue halves for all 128 rows (fixed
+    // ownership and summation order: bit-reproducible, no atomics).  Lane l reads 8 bytes (4 columns) of row i*8 + l/4;
+    // the 8 row-lanes are folded by shuffles and lanes 0..3 add to the shared-memory accumulators they alone own.
+    if (do_stats) {
+      const int wq = warp - 12;
+      const int piece = lane & 3;
+      const int chunk = wq * 2 + (piece >> 1);
+      const int r0 = lane >> 2;
+      const int soff = r0 * 128 + ((chunk ^ r0) << 4) + (piece & 1) * 8;
+      constexpr int NCH = BN / 32;
+      constexpr int split_at = 2 * ((BN / 64 + 1) / 2);
+      constexpr int spt_h[2] = {split_at / 2, (NCH - split_at) / 2};
+      int sb[2] = {0, 0};
+      uint32_t st_phase[2] = {0u, 0u};
+      named_bar_sync(3, 384);            // accumulators zeroed by the epilogue warps
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int n0 = (w % num_n) * BN;
+#pragma unroll 1
+        for (int j = 0; j < spt_h[0]; ++j) {
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            if (j >= spt_h[h]) continue;
+            const int b = sb[h];
+            mbar_wait(&staged_bar[h * kMaxStoreBufs + b], (st_phase[h] >> b) & 1u);
+            const uint8_t* const sp = sD + (h * NB + b) * kStoreBufBytes + soff;
+            float sx[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint2 w2 = *reinterpret_cast<const uint2*>(sp + i * 1024);
+              const float a0 = __uint_as_float(w2.x << 16), a1 = __uint_as_float(w2.x & 0xffff0000u);
+              const float b0 = __uint_as_float(w2.y << 16), b1 = __uint_as_float(w2.y & 0xffff0000u);
+              sx[0] += a0; sq[0] = fmaf(a0, a0, sq[0]);
+              sx[1] += a1; sq[1] = fmaf(a1, a1, sq[1]);
+              sx[2] += b0; sq[2] = fmaf(b0, b0, sq[2]);
+              sx[3] += b1; sq[3] = fmaf(b1, b1, sq[3]);
+            }
+            // the slice is read: the epilogue may reuse it (after its TMA store has drained it too)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sdone_bar[h * kMaxStoreBufs + b]);
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], o);
+                sq[k] += __shfl_xor_sync(0xffffffffu, sq[k], o);
+              }
+            }
+            const int gcol = n0 + ((h ? split_at : 0) / 2 + j) * 64 + wq * 16 + piece * 4;
+            if (lane < 4 && gcol < p.N) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                sStat[gcol + k] += sx[k];
+                sStat[p.N + gcol + k] += sq[k];
+              }
+            }
+            st_phase[h] ^= (1u << b);
+            sb[h] = (b + 1 == NB) ? 0 : b + 1;
+          }
+        }
+      }
+      named_bar_sync(3, 384);            // all slices accumulated: the epilogue warps write the partial row
     }
   }
 
