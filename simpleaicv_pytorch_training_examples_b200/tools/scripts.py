@@ -40,7 +40,9 @@ def train_classification(train_loader, model, criterion, optimizer, scheduler, e
     world = _world()
     iter_index = 1
     from .utils import CudaPrefetcher
-    for _, data in enumerate(CudaPrefetcher(train_loader)):
+    # config.device_normalize = (mean, std): uint8 [B, H, W, 3] batches (classification.common.Uint8ClassificationCollater)
+    # are normalised on the device by the prefetcher; fp32 batches pass through unchanged
+    for _, data in enumerate(CudaPrefetcher(train_loader, normalize=getattr(config, 'device_normalize', None))):
         images, labels = data['image'], data['label']
         bad = (~torch.isfinite(images)).any()
         if labels.dtype.is_floating_point:
@@ -117,7 +119,9 @@ def train_epoch_with_loss_terms(train_loader, model, criterion, optimizer, sched
     world = _world()
     iter_index = 1
     from .utils import CudaPrefetcher
-    for _, data in enumerate(CudaPrefetcher(train_loader)):
+    # config.device_normalize = (mean, std): uint8 [B, H, W, 3] batches (classification.common.Uint8ClassificationCollater)
+    # are normalised on the device by the prefetcher; fp32 batches pass through unchanged
+    for _, data in enumerate(CudaPrefetcher(train_loader, normalize=getattr(config, 'device_normalize', None))):
         loss_value, checked, batch = compute(data)
         bad = torch.zeros((), dtype=torch.bool, device=next(iter(loss_value.values())).device)
         for t in checked:

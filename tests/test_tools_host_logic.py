@@ -174,7 +174,7 @@ def test_dict_loss_epoch_body_guards_accumulation_and_schedule(monkeypatch):
     (reference tools/scripts.py:900-1092).  Host logic only: a torch Linear on CPU stands in for the model."""
     import logging
     from simpleaicv_pytorch_training_examples_b200.tools import scripts, utils as tutils
-    monkeypatch.setattr(tutils, 'CudaPrefetcher', lambda loader: loader)
+    monkeypatch.setattr(tutils, 'CudaPrefetcher', lambda loader, **kw: loader)
     torch.manual_seed(0)
     model = torch.nn.Linear(4, 2)
     ref = torch.nn.Linear(4, 2)
