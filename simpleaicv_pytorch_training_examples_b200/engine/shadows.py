@@ -30,7 +30,8 @@ def _walk(obj, seen, out, depth=0):
 
 
 def collect(rt):
-    """[(parameter, bf16 shadow tensor, conv layout (c, taps, cp, kpad) or None)] of the runtime `rt` (after rt.prep())."""
+    """[(parameter, bf16 shadow tensor, conv layout (c, taps, cp, kpad) or None, owner object holding it as `w_bf16`)] of the
+    runtime `rt` (after rt.prep())."""
     rt.prep()
     units, res = [], []
     _walk(rt, set(), units)
@@ -38,7 +39,7 @@ def collect(rt):
         if isinstance(u, ConvBN):
             if u.is_stem or u.w_bf16 is None:
                 continue
-            res.append((u.conv.weight, u.w_bf16, (u.c, u.r * u.s, u.cp, u.kpad)))
+            res.append((u.conv.weight, u.w_bf16, (u.c, u.r * u.s, u.cp, u.kpad), u))
             continue
         mod = getattr(u, 'mod', None) or getattr(u, 'fc', None) or getattr(u, 'conv', None)
         w = getattr(mod, 'weight', None)
@@ -46,5 +47,5 @@ def collect(rt):
         if not plain or u.w_bf16 is None or u.w_bf16.dim() != 2 or u.w_bf16.shape[1] != w.shape[1] or \
                 u.w_bf16.shape[0] < w.shape[0] or not u.w_bf16.is_contiguous():
             continue
-        res.append((w, u.w_bf16, None))
+        res.append((w, u.w_bf16, None, u))
     return res

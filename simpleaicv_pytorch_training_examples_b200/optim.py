@@ -57,10 +57,18 @@ class _FusedBase(torch.optim.Optimizer):
         self._pending = None
 
     # ---- shadows (called by the runtimes: engine/convnet.py, engine/vit.py)
-    def register_shadow(self, param, shadow, conv=None):
+    def register_shadow(self, param, shadow, conv=None, owner=None):
+        """owner: the runtime object whose ``w_bf16`` attribute is this copy; when given, the attribute is re-read before
+        every step, so a copy the runtime re-allocates (device move) is followed instead of silently going stale."""
         assert shadow.dtype == torch.bfloat16 and shadow.is_contiguous()
-        self._shadows[id(param)] = (shadow, conv)
+        self._shadows[id(param)] = (shadow, conv, owner)
         self._key = None
+
+    def _follow_owners(self):
+        for pid, (shadow, conv, owner) in list(self._shadows.items()):
+            cur = getattr(owner, 'w_bf16', None) if owner is not None else shadow
+            if cur is not None and cur is not shadow:
+                self._shadows[pid] = (cur, conv, owner)
 
     def attach(self, model):
         """Registers the operand copies of every weight of `model`'s runtime (a no-op for plain torch modules)."""
@@ -68,9 +76,9 @@ class _FusedBase(torch.optim.Optimizer):
         if hasattr(m, '_runtime'):
             from .engine import shadows
             mine = {id(p) for g in self.param_groups for p in g['params']}
-            for param, shadow, conv in shadows.collect(m._runtime()):
+            for param, shadow, conv, owner in shadows.collect(m._runtime()):
                 if id(param) in mine:
-                    self.register_shadow(param, shadow, conv)
+                    self.register_shadow(param, shadow, conv, owner=owner)
         return self
 
     # ---- table
@@ -126,6 +134,7 @@ class _FusedBase(torch.optim.Optimizer):
         plist = self._params()
         if not plist:
             return None
+        self._follow_owners()
         key = tuple((id(p), p.data_ptr(), p.grad.data_ptr(), self._shadows.get(id(p), (None,))[0] is not None and
                      self._shadows[id(p)][0].data_ptr()) for _, p in plist)
         if key != self._key:
