@@ -224,3 +224,96 @@ def test_dict_loss_epoch_body_guards_accumulation_and_schedule(monkeypatch):
     assert len(sched.calls) == len(totals) == 2
     assert sched.calls == [2 / 6 + 2, 4 / 6 + 2]
     assert abs(avg - 2 * sum(totals) / len(totals)) < 1e-6
+
+
+def test_mae_and_distillation_epoch_bodies(monkeypatch):
+    """train_mae_self_supervised_learning (reference tools/scripts.py:1774-1934: `outputs, masks = model(images)`,
+    `criterion(outputs, labels, masks)`) and train_distill_classification (:291-500: dict of losses, CE on the student - and
+    on the teacher only when it is not frozen - every other loss on (student, teacher), each weighted by config.loss_ratio;
+    the frozen teacher stays in eval mode).  Host logic only: small torch modules on CPU stand in for the models."""
+    import logging
+    from simpleaicv_pytorch_training_examples_b200.distillation import losses as kd_losses
+    from simpleaicv_pytorch_training_examples_b200.masked_image_modeling import losses as mim_losses
+    from simpleaicv_pytorch_training_examples_b200.tools import scripts, utils as tutils
+    monkeypatch.setattr(tutils, 'CudaPrefetcher', lambda loader, **kw: loader)
+    log = logging.getLogger('t')
+
+    class Loader(list):
+        dataset = list(range(12))
+
+    class Sched:
+        current_lr = 0.1
+
+        def __init__(self):
+            self.calls = []
+
+        def step(self, optimizer, epoch):
+            self.calls.append(epoch)
+
+    class Cfg:
+        accumulation_steps, batch_size, print_interval, local_rank = 1, 4, 1, 0
+        freeze_teacher = True
+        loss_ratio = {'CELoss': 1.0, 'KDLoss': 0.5}
+
+    # ---- MAE: model returns (pred, mask)
+    class FakeMAE(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(6, 6)
+
+        def forward(self, x):
+            return self.lin(x), (x[..., 0] > 0).float()
+
+    torch.manual_seed(0)
+    mae, ref = FakeMAE(), FakeMAE()
+    ref.load_state_dict(mae.state_dict())
+    g = torch.Generator().manual_seed(2)
+    batches = [{'image': torch.randn(4, 5, 6, generator=g), 'label': torch.randn(4, 5, 6, generator=g)} for _ in range(3)]
+    opt, ropt = torch.optim.SGD(mae.parameters(), lr=0.1), torch.optim.SGD(ref.parameters(), lr=0.1)
+    crit = mim_losses.MSELoss()
+    sched = Sched()
+    avg = scripts.train_mae_self_supervised_learning(Loader(batches), mae, crit, opt, sched, 1, log, Cfg)
+    vals = []
+    for b in batches:
+        out, mask = ref(b['image'])
+        loss = crit(out, b['label'], mask)
+        loss.backward()
+        ropt.step()
+        ropt.zero_grad()
+        vals.append(float(loss))
+    for p, q in zip(mae.parameters(), ref.parameters()):
+        torch.testing.assert_close(p, q)
+    assert abs(avg - sum(vals) / 3) < 1e-6 and len(sched.calls) == 3
+
+    # ---- distillation: model returns (teacher logits, student logits)
+    class FakeKD(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.teacher, self.student = torch.nn.Linear(6, 5), torch.nn.Linear(6, 5)
+            for p in self.teacher.parameters():
+                p.requires_grad = False
+
+        def forward(self, x):
+            with torch.no_grad():
+                t = self.teacher(x)
+            return t, self.student(x)
+
+    kd, kref = FakeKD(), FakeKD()
+    kref.load_state_dict(kd.state_dict())
+    batches = [{'image': torch.randn(4, 6, generator=g), 'label': torch.randint(0, 5, (4,), generator=g)} for _ in range(3)]
+    crit = {'CELoss': kd_losses.CELoss(), 'KDLoss': kd_losses.KDLoss(2.0)}
+    opt = torch.optim.SGD([p for p in kd.parameters() if p.requires_grad], lr=0.1)
+    ropt = torch.optim.SGD([p for p in kref.parameters() if p.requires_grad], lr=0.1)
+    avg = scripts.train_distill_classification(Loader(batches), kd, crit, opt, Sched(), 1, log, Cfg)
+    assert not kd.teacher.training and kd.student.training
+    vals = []
+    for b in batches:
+        t, s = kref(b['image'])
+        loss = crit['CELoss'](s, b['label']) * 1.0 + crit['KDLoss'](s, t) * 0.5
+        loss.backward()
+        ropt.step()
+        ropt.zero_grad()
+        vals.append(float(loss))
+    for p, q in zip(kd.student.parameters(), kref.student.parameters()):
+        torch.testing.assert_close(p, q)
+    assert abs(avg - sum(vals) / 3) < 1e-6
