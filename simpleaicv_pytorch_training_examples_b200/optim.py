@@ -81,6 +81,11 @@ class _FusedBase(torch.optim.Optimizer):
                     self.register_shadow(param, shadow, conv, owner=owner)
         return self
 
+    def load_state_dict(self, state_dict):
+        """torch's loader replaces the state tensors (momentum buffers, moments): the device table must be rebuilt."""
+        super().load_state_dict(state_dict)
+        self._key = None
+
     # ---- table
     def _params(self):
         out = []

@@ -83,6 +83,24 @@ def test_fused_step_matches_torch(kind, unaligned):
         assert torch.equal(ref2.state[p][key], mine.state[q][key])
     if kind == 'adamw':
         assert float(ref2.state[pa[0]]['step']) == 12.
+    # resume: load torch.optim's state into the fused optimizer in the middle of a run (the loader replaces the state
+    # tensors, so the device table must follow) and keep stepping in lockstep
+    # (deep copy: torch's loader keeps tensors that already have the parameter's dtype / device, i.e. it would ALIAS the two
+    # optimizers' momentum buffers; a checkpoint read with torch.load never aliases)
+    import copy
+    mine.load_state_dict(copy.deepcopy(ref.state_dict()))
+    for step in range(12, 15):
+        for opt in (ref, mine):
+            for gi, g in enumerate(opt.param_groups):
+                g['lr'] = (0.1 if kind != 'adamw' else 1e-2) * (1 + gi) * 0.9 ** step
+        for p, q, g in zip(pa, pb, _grads(pa, step, unaligned)):
+            p.grad, q.grad = g.clone(), g
+        ref.step()
+        mine.step()
+    torch.cuda.synchronize()
+    for i, (p, q) in enumerate(zip(pa, pb)):
+        err = (p - q).abs().max().item()
+        assert err <= 1e-5 * p.abs().max().item() + 1e-7, f'{kind} after resume, tensor {i}: max abs diff {err}'
 
 
 def test_fused_clip_matches_clip_grad_norm():
